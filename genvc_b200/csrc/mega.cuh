@@ -1,0 +1,52 @@
+// Parameters of the fused persistent decode kernel (decode_mega.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ops.cuh"
+#include "stream_layout.h"
+
+namespace gv {
+
+struct MegaParams {
+    int L, D, H, V, Vpad, S_max;
+    int P;          // prefix length: cache row of mel position n is P + n
+    int n_steps;    // tokens to emit in this launch (at most)
+    int nslot;      // ring depth
+    // weights
+    const float* stream;  // per-CTA weight streams (stream_layout.h)
+    const float* blob;    // reference-layout blob (LayerNorm params, embeddings)
+    long long ln1_off, ln2_off, layer_stride, lnf_off, mel_emb_off, mel_pos_off;
+    // activations / state (global, L2-resident)
+    float* kv;
+    long long kv_layer_stride;  // floats per (layer, k|v) plane
+    float* x;       // [D] residual stream
+    float* qbuf;    // [D]
+    float* ubuf;    // [4D]
+    float* att_o;   // [items][hd] un-normalised partial outputs
+    float* att_ml;  // [items][2]  (max, sum)
+    float* pend_logits;  // [V]
+    float* pend_latent;  // [D]
+    GenState* st;
+    unsigned char* seen;  // [Vpad]
+    unsigned* barrier;
+    // sampling
+    int top_k;
+    float top_p, top_p_threshold, temperature, rep_penalty;
+    int ignore_eos, stop_token, max_total;
+    unsigned long long seed;
+    const float* noise;        // [n_steps, V] or null
+    const long long* forced;   // [n_steps] or null
+    // outputs
+    long long* ids_out;   // [n_steps]
+    float* latents_out;   // [n_steps, D]
+    float* logits_out;    // [n_steps, V] or null
+    int* status;          // {emitted, done}
+};
+
+size_t mega_smem_bytes(int D, int nslot, int Vpad);
+cudaError_t launch_decode_mega(const MegaParams& p, int grid, cudaStream_t st);
+cudaError_t launch_pack_stream(const StreamDims& s, int layer, int ph, const float* W, const float* bias, int w_nk,
+                               float* stream, cudaStream_t st);
+
+}  // namespace gv
