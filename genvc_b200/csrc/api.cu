@@ -1,0 +1,589 @@
+// C ABI of libgenvc_b200.so (include/genvc_b200.h): context, weight-blob layout, and the host-side
+// orchestration of the path — perceiver, prefix embedding, prefill, decode (fused persistent kernel
+// or per-op kernels), teacher-forced latent pass.  No torch types; the caller owns device memory.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/genvc_b200.h"
+#include "layout.h"
+#include "mega.cuh"
+#include "ops.cuh"
+#include "stream_layout.h"
+
+using namespace gv;
+
+namespace {
+
+constexpr size_t kSplitKFloats = size_t(4) << 20;  // deterministic split-K partials (ops.cu)
+constexpr int kMegaSlots = 12;
+
+struct Workspace {
+    size_t bytes = 0;
+    size_t take(size_t n, size_t align = 256) {
+        bytes = (bytes + align - 1) / align * align;
+        size_t o = bytes;
+        bytes += n;
+        return o;
+    }
+};
+
+}  // namespace
+
+struct genvc_ctx {
+    genvc_config cfg;
+    int device = 0;
+    int n_sm = 0;
+    int grid = 0;  // CTAs of the fused decode kernel
+    bool mega_ok = false;
+    Layout layout;
+    StreamDims sdims;
+    mutable std::string err;
+    unsigned long long nlaunch = 0;
+
+    const float* blob = nullptr;
+    float* stream = nullptr;
+    bool stream_packed = false;
+    float* kv = nullptr;
+    char* ws = nullptr;
+
+    // workspace offsets (bytes)
+    size_t o_barrier, o_state, o_seen, o_status_scratch, o_pend_logits, o_pend_latent, o_mx, o_mq, o_mu, o_matt_o, o_matt_ml,
+        o_splitk, o_X, o_A, o_QKV, o_U;
+    size_t o_pc_melT, o_pc_ctx, o_pc_kv, o_pc_lat, o_pc_q, o_pc_o, o_pc_h, o_pc_g;
+    size_t ws_bytes = 0;
+    int Vpad = 0;
+
+    // host mirror of the generation state
+    int B = 0, P = 0;
+    bool prefilled = false, pending = false;
+    int n_host = 0;
+
+    int D() const { return cfg.d_model; }
+    int H() const { return cfg.n_head; }
+    int hd() const { return cfg.d_model / cfg.n_head; }
+    int V() const { return cfg.n_audio_vocab; }
+    size_t rows_cap() const { return (size_t)cfg.max_batch * cfg.max_seq; }
+    size_t kv_plane() const { return (size_t)cfg.max_batch * cfg.d_model * cfg.max_seq; }  // floats per (layer, k|v)
+    size_t kv_batch_stride() const { return (size_t)cfg.d_model * cfg.max_seq; }
+
+    template <class T>
+    T* at(size_t off) const {
+        return reinterpret_cast<T*>(ws + off);
+    }
+    const float* w(uint64_t off) const { return blob + off; }
+
+    int fail(int code, const char* fmt, ...) const {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return ctx->fail(GENVC_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                             __LINE__);                                                                       \
+    } while (0)
+
+static bool valid_hd(int hd) { return hd == 32 || hd == 64 || hd == 128 || hd == 256; }
+
+static void plan_workspace(genvc_ctx* c) {
+    const genvc_config& g = c->cfg;
+    const size_t D = g.d_model, V = g.n_audio_vocab, MB = g.max_batch, F = sizeof(float);
+    c->Vpad = (int)((V + 15) / 16 * 16);
+    Workspace w;
+    c->o_barrier = w.take(256);
+    c->o_state = w.take(sizeof(GenState) + 64);
+    c->o_seen = w.take(MB * c->Vpad);
+    c->o_status_scratch = w.take(64);
+    c->o_pend_logits = w.take(MB * V * F);
+    c->o_pend_latent = w.take(MB * D * F);
+    c->o_mx = w.take(D * F);
+    c->o_mq = w.take(D * F);
+    c->o_mu = w.take(4 * D * F);
+    const size_t items = (size_t)std::max(c->grid, 1) + g.n_head;
+    c->o_matt_o = w.take(items * (D / g.n_head) * F);
+    c->o_matt_ml = w.take(items * 2 * F);
+    c->o_splitk = w.take(kSplitKFloats * F);
+    const size_t R = c->rows_cap();
+    c->o_X = w.take(R * D * F);
+    c->o_A = w.take(R * D * F);
+    c->o_QKV = w.take(R * 3 * D * F);
+    c->o_U = w.take(R * 4 * D * F);
+    // perceiver
+    const size_t S = g.max_mel_frames, NL = g.pc_latents, inner = (size_t)g.pc_dim_head * g.pc_heads;
+    const size_t Rc = MB * (NL + S);
+    c->o_pc_melT = w.take(MB * S * g.pc_dim_context * F);
+    c->o_pc_ctx = w.take(Rc * D * F);
+    c->o_pc_kv = w.take(Rc * 2 * inner * F);
+    c->o_pc_lat = w.take(MB * NL * D * F);
+    c->o_pc_q = w.take(MB * NL * inner * F);
+    c->o_pc_o = w.take(MB * NL * inner * F);
+    c->o_pc_h = w.take(MB * NL * 2 * g.pc_ff_inner * F);
+    c->o_pc_g = w.take(MB * NL * c->layout.pc_ff_inner_pad * F);
+    c->ws_bytes = (w.bytes + 255) / 256 * 256;
+}
+
+extern "C" {
+
+int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
+    if (!cfg || !out) return GENVC_E_INVALID;
+    *out = nullptr;
+    genvc_ctx* ctx = new (std::nothrow) genvc_ctx();
+    if (!ctx) return GENVC_E_INVALID;
+    ctx->cfg = *cfg;
+    ctx->device = device;
+    const genvc_config& g = ctx->cfg;
+    auto bad = [&](const char* why) {
+        // the context is returned so the caller can read the message, then destroy it
+        *out = ctx;
+        return ctx->fail(GENVC_E_INVALID, "genvc_create: %s", why);
+    };
+    if (g.n_layer <= 0 || g.d_model <= 0 || g.n_head <= 0 || g.d_model % g.n_head) return bad("bad n_layer/d_model/n_head");
+    if (g.d_model % 128 || g.d_model > 1024) return bad("d_model must be a multiple of 128 and <= 1024");
+    if (!valid_hd(g.d_model / g.n_head)) return bad("head_dim must be 32, 64, 128 or 256");
+    if (g.n_audio_vocab <= 0 || g.n_audio_vocab > 2048) return bad("n_audio_vocab must be in (0, 2048]");
+    if (g.max_batch <= 0 || g.max_batch > GV_MAX_BATCH) return bad("max_batch must be in [1, 64]");
+    if (g.max_seq <= 0 || g.max_mel_frames <= 0) return bad("max_seq / max_mel_frames must be positive");
+    if (!valid_hd(g.pc_dim_head) || g.pc_dim_context % 4 || g.pc_latents <= 0 || g.pc_depth <= 0 || g.pc_ff_inner <= 0)
+        return bad("unsupported perceiver shape");
+    if (g.start_audio < 0 || g.start_audio >= g.n_audio_vocab || g.stop_audio < 0 || g.stop_audio >= g.n_audio_vocab)
+        return bad("start/stop audio token outside the vocabulary");
+    ctx->layout.build(g);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e == cudaSuccess && device >= 0 && device < ndev) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->n_sm = prop.multiProcessorCount;
+    } else {
+        (void)cudaGetLastError();
+    }
+    // Without a device (CPU-only layout queries) the grid defaults to a B200's 148 SMs.
+    ctx->grid = ctx->n_sm > 0 ? ctx->n_sm : 148;
+    ctx->sdims = StreamDims{g.n_layer, g.d_model, g.n_audio_vocab, ctx->grid};
+    // column-slice limits of the fused kernel's register tiles (decode_mega.cu: MAXT * CT)
+    auto ceil_div = [](int a, int b) { return (a + b - 1) / b; };
+    ctx->mega_ok = ceil_div(4 * g.d_model, ctx->grid) <= 32 && ceil_div(g.d_model, ctx->grid) <= 8 &&
+                   ceil_div(g.n_audio_vocab, ctx->grid) <= 32 && g.n_audio_vocab <= 2048;
+    plan_workspace(ctx);
+    *out = ctx;
+    return GENVC_OK;
+}
+
+void genvc_destroy(genvc_ctx* ctx) { delete ctx; }
+
+const char* genvc_last_error(const genvc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int genvc_decode_grid(const genvc_ctx* ctx) { return ctx ? ctx->grid : 0; }
+
+uint64_t genvc_blob_floats(const genvc_ctx* ctx) { return ctx ? ctx->layout.total : 0; }
+int genvc_num_tensors(const genvc_ctx* ctx) { return ctx ? (int)ctx->layout.tensors.size() : 0; }
+
+int genvc_tensor_name(const genvc_ctx* ctx, int index, char* buf, size_t buf_len) {
+    if (!ctx || !buf || index < 0 || index >= (int)ctx->layout.tensors.size()) return GENVC_E_INVALID;
+    const std::string& n = ctx->layout.tensors[index].name;
+    if (n.size() + 1 > buf_len) return GENVC_E_INVALID;
+    memcpy(buf, n.c_str(), n.size() + 1);
+    return GENVC_OK;
+}
+
+int genvc_tensor_info(const genvc_ctx* ctx, const char* key, uint64_t* offset, uint64_t* rows, uint64_t* cols,
+                      uint64_t* row_stride) {
+    if (!ctx || !key) return GENVC_E_INVALID;
+    auto it = ctx->layout.index.find(key);
+    if (it == ctx->layout.index.end()) return ctx->fail(GENVC_E_INVALID, "unknown tensor '%s'", key);
+    const TensorEntry& t = ctx->layout.tensors[it->second];
+    if (offset) *offset = t.off;
+    if (rows) *rows = t.rows;
+    if (cols) *cols = t.cols;
+    if (row_stride) *row_stride = t.stride;
+    return GENVC_OK;
+}
+
+int genvc_bind_weights(genvc_ctx* ctx, const float* blob_dev, uint64_t n_floats) {
+    if (!ctx) return GENVC_E_INVALID;
+    if (!blob_dev || n_floats < ctx->layout.total) return ctx->fail(GENVC_E_INVALID, "weight blob too small");
+    if (reinterpret_cast<uintptr_t>(blob_dev) % 128) return ctx->fail(GENVC_E_INVALID, "weight blob must be 128-byte aligned");
+    ctx->blob = blob_dev;
+    ctx->stream_packed = false;
+    return GENVC_OK;
+}
+
+uint64_t genvc_stream_floats(const genvc_ctx* ctx) {
+    if (!ctx || !ctx->mega_ok) return 0;
+    return (uint64_t)stream_total_floats(ctx->sdims);
+}
+
+int genvc_pack_stream(genvc_ctx* ctx, float* stream_dev, uint64_t n_floats, void* stream) {
+    if (!ctx) return GENVC_E_INVALID;
+    if (!ctx->mega_ok) return ctx->fail(GENVC_E_UNSUPPORTED, "fused decode kernel does not support this shape");
+    if (!ctx->blob) return ctx->fail(GENVC_E_STATE, "bind weights first");
+    if (!stream_dev || n_floats < genvc_stream_floats(ctx) || reinterpret_cast<uintptr_t>(stream_dev) % 128)
+        return ctx->fail(GENVC_E_INVALID, "decode stream buffer too small or misaligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    const Layout& L = ctx->layout;
+    for (int l = 0; l < ctx->cfg.n_layer; ++l) {
+        const LayerOff& o = L.layers[l];
+        CK(launch_pack_stream(ctx->sdims, l, PH_QKV, ctx->w(o.attn_w), ctx->w(o.attn_b), 0, stream_dev, st));
+        CK(launch_pack_stream(ctx->sdims, l, PH_PROJ, ctx->w(o.proj_w), ctx->w(o.proj_b), 0, stream_dev, st));
+        CK(launch_pack_stream(ctx->sdims, l, PH_FC, ctx->w(o.fc_w), ctx->w(o.fc_b), 0, stream_dev, st));
+        CK(launch_pack_stream(ctx->sdims, l, PH_PROJ2, ctx->w(o.proj2_w), ctx->w(o.proj2_b), 0, stream_dev, st));
+        ctx->nlaunch += 4;
+    }
+    CK(launch_pack_stream(ctx->sdims, 0, PH_HEAD, ctx->w(L.mel_head_w), ctx->w(L.mel_head_b), 1, stream_dev, st));
+    ctx->nlaunch += 1;
+    ctx->stream = stream_dev;
+    ctx->stream_packed = true;
+    return GENVC_OK;
+}
+
+uint64_t genvc_kv_floats(const genvc_ctx* ctx) { return ctx ? (uint64_t)ctx->cfg.n_layer * 2 * ctx->kv_plane() : 0; }
+uint64_t genvc_workspace_bytes(const genvc_ctx* ctx) { return ctx ? ctx->ws_bytes : 0; }
+
+int genvc_bind_buffers(genvc_ctx* ctx, float* kv_dev, uint64_t kv_floats, void* workspace_dev, uint64_t workspace_bytes) {
+    if (!ctx) return GENVC_E_INVALID;
+    if (!kv_dev || kv_floats < genvc_kv_floats(ctx)) return ctx->fail(GENVC_E_INVALID, "KV cache buffer too small");
+    if (!workspace_dev || workspace_bytes < ctx->ws_bytes) return ctx->fail(GENVC_E_INVALID, "workspace too small");
+    if (reinterpret_cast<uintptr_t>(kv_dev) % 128 || reinterpret_cast<uintptr_t>(workspace_dev) % 256)
+        return ctx->fail(GENVC_E_INVALID, "KV cache / workspace misaligned");
+    ctx->kv = kv_dev;
+    ctx->ws = static_cast<char*>(workspace_dev);
+    ctx->prefilled = false;
+    return GENVC_OK;
+}
+
+uint64_t genvc_launch_count(const genvc_ctx* ctx) { return ctx ? ctx->nlaunch : 0; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// helpers shared by prefill / latent pass / per-op decode
+// ---------------------------------------------------------------------------------------------
+static int check_ready(genvc_ctx* ctx) {
+    if (!ctx) return GENVC_E_INVALID;
+    if (!ctx->blob) return ctx->fail(GENVC_E_STATE, "weights not bound");
+    if (!ctx->kv || !ctx->ws) return ctx->fail(GENVC_E_STATE, "buffers not bound");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return ctx->fail(GENVC_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return GENVC_OK;
+}
+
+static GemmArgs gemm(const float* A, int lda, const float* W, int ldw, int w_nk, const float* bias, const float* res, int ldr,
+                     float* C, int ldc, int M, int N, int K, int act) {
+    GemmArgs a;
+    a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.w_nk = w_nk; a.bias = bias; a.residual = res; a.ldr = ldr;
+    a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K; a.act = act;
+    return a;
+}
+
+// The 30 pre-LN blocks over rows X [B, M, D] (contiguous, R = B*M rows).
+//   pos0 >= 0: rows are positions pos0..pos0+M-1 of the KV cache: K/V are appended and attention runs
+//              against the cache (decode, M == 1) or over the rows themselves (prefill, pos0 == 0);
+//   pos0 <  0: uncached causal pass (teacher-forced latent pass).
+static int run_blocks(genvc_ctx* ctx, int B, int M, int pos0, const int* skip, cudaStream_t st) {
+    const genvc_config& g = ctx->cfg;
+    const int D = g.d_model, H = g.n_head, hd = D / H, R = B * M;
+    float* X = ctx->at<float>(ctx->o_X);
+    float* A = ctx->at<float>(ctx->o_A);
+    float* QKV = ctx->at<float>(ctx->o_QKV);
+    float* U = ctx->at<float>(ctx->o_U);
+    float* sk = ctx->at<float>(ctx->o_splitk);
+    unsigned long long* nl = &ctx->nlaunch;
+    const float scale = 1.0f / sqrtf((float)hd);
+    for (int l = 0; l < g.n_layer; ++l) {
+        const LayerOff& o = ctx->layout.layers[l];
+        float* kc = ctx->kv + ((size_t)l * 2 + 0) * ctx->kv_plane();
+        float* vc = ctx->kv + ((size_t)l * 2 + 1) * ctx->kv_plane();
+        CK(launch_layernorm(X, D, 0, A, D, 0, R, R, D, ctx->w(o.ln1_w), ctx->w(o.ln1_b), nullptr, nullptr, skip, st, nl));
+        CK(launch_gemm(gemm(A, D, ctx->w(o.attn_w), 3 * D, 0, ctx->w(o.attn_b), nullptr, 0, QKV, 3 * D, R, 3 * D, D, ACT_NONE),
+                       sk, kSplitKFloats, skip, st, nl));
+        if (pos0 >= 0)
+            CK(launch_kv_scatter(QKV, B, M, D, H, kc, vc, (long)ctx->kv_batch_stride(), g.max_seq, pos0, skip, st, nl));
+        if (pos0 >= 0 && M == 1) {
+            // single-token decode against the cache (positions 0..pos0)
+            CK(launch_kv_attention(QKV, 3L * D, kc, vc, (long)ctx->kv_batch_stride(), B, H, hd, pos0 + 1, g.max_seq, A, D, skip,
+                                   st, nl));
+        } else {
+            AttnArgs a;
+            a.Q = QKV;         a.q_bs = (long)M * 3 * D; a.q_rs = 3 * D; a.q_hs = hd;
+            a.K = QKV + D;     a.k_bs = (long)M * 3 * D; a.k_rs = 3 * D; a.k_hs = hd;
+            a.V = QKV + 2 * D; a.v_bs = (long)M * 3 * D; a.v_rs = 3 * D; a.v_hs = hd;
+            a.O = A;           a.o_bs = (long)M * D;     a.o_rs = D;     a.o_hs = hd;
+            a.B = B; a.H = H; a.M = M; a.hd = hd; a.n_keys = M; a.causal = 1; a.pos0 = 0; a.scale = scale;
+            CK(launch_attention(a, skip, st, nl));
+        }
+        CK(launch_gemm(gemm(A, D, ctx->w(o.proj_w), D, 0, ctx->w(o.proj_b), X, D, X, D, R, D, D, ACT_NONE), sk, kSplitKFloats,
+                       skip, st, nl));
+        CK(launch_layernorm(X, D, 0, A, D, 0, R, R, D, ctx->w(o.ln2_w), ctx->w(o.ln2_b), nullptr, nullptr, skip, st, nl));
+        CK(launch_gemm(gemm(A, D, ctx->w(o.fc_w), 4 * D, 0, ctx->w(o.fc_b), nullptr, 0, U, 4 * D, R, 4 * D, D, ACT_GELU_NEW), sk,
+                       kSplitKFloats, skip, st, nl));
+        CK(launch_gemm(gemm(U, 4 * D, ctx->w(o.proj2_w), D, 0, ctx->w(o.proj2_b), X, D, X, D, R, D, 4 * D, ACT_NONE), sk,
+                       kSplitKFloats, skip, st, nl));
+    }
+    return GENVC_OK;
+}
+
+// ln_f -> final_norm of row `row` of each batch element -> pending latent; mel_head -> pending logits
+static int run_head(genvc_ctx* ctx, int B, int M, int row, const int* skip, cudaStream_t st) {
+    const genvc_config& g = ctx->cfg;
+    const int D = g.d_model, V = g.n_audio_vocab;
+    const Layout& L = ctx->layout;
+    float* X = ctx->at<float>(ctx->o_X);
+    float* lat = ctx->at<float>(ctx->o_pend_latent);
+    float* lg = ctx->at<float>(ctx->o_pend_logits);
+    CK(launch_layernorm(X + (size_t)row * D, D, (long)M * D, lat, D, D, B, 1, D, ctx->w(L.lnf_w), ctx->w(L.lnf_b), ctx->w(L.fn_w),
+                        ctx->w(L.fn_b), skip, st, &ctx->nlaunch));
+    CK(launch_gemm(gemm(lat, D, ctx->w(L.mel_head_w), D, 1, ctx->w(L.mel_head_b), nullptr, 0, lg, V, B, V, D, ACT_NONE),
+                   ctx->at<float>(ctx->o_splitk), kSplitKFloats, skip, st, &ctx->nlaunch));
+    return GENVC_OK;
+}
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------
+// perceiver
+// ---------------------------------------------------------------------------------------------
+int genvc_perceiver(genvc_ctx* ctx, const float* mel_dev, int B, int S_mel, float* latents_out_dev, void* stream) {
+    if (int rc = check_ready(ctx)) return rc;
+    const genvc_config& g = ctx->cfg;
+    if (!mel_dev || !latents_out_dev) return ctx->fail(GENVC_E_INVALID, "null pointer");
+    if (B <= 0 || B > g.max_batch) return ctx->fail(GENVC_E_INVALID, "batch %d outside [1, %d]", B, g.max_batch);
+    if (S_mel <= 0 || S_mel > g.max_mel_frames)
+        return ctx->fail(GENVC_E_INVALID, "mel frames %d outside [1, %d]", S_mel, g.max_mel_frames);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout& L = ctx->layout;
+    const int D = g.d_model, C = g.pc_dim_context, NL = g.pc_latents, inner = g.pc_dim_head * g.pc_heads;
+    const int ffi = g.pc_ff_inner, ffp = (int)L.pc_ff_inner_pad;
+    const int RC = NL + S_mel;  // context rows per batch element
+    float* melT = ctx->at<float>(ctx->o_pc_melT);
+    float* cx = ctx->at<float>(ctx->o_pc_ctx);
+    float* kvb = ctx->at<float>(ctx->o_pc_kv);
+    float* lat = ctx->at<float>(ctx->o_pc_lat);
+    float* q = ctx->at<float>(ctx->o_pc_q);
+    float* ob = ctx->at<float>(ctx->o_pc_o);
+    float* hb = ctx->at<float>(ctx->o_pc_h);
+    float* gb = ctx->at<float>(ctx->o_pc_g);
+    float* sk = ctx->at<float>(ctx->o_splitk);
+    unsigned long long* nl = &ctx->nlaunch;
+
+    CK(launch_transpose_mel(mel_dev, B, C, S_mel, melT, st, nl));
+    for (int b = 0; b < B; ++b)  // proj_context into rows NL.. of this element's context block
+        CK(launch_gemm(gemm(melT + (size_t)b * S_mel * C, C, ctx->w(L.pc_proj_w), C, 1, ctx->w(L.pc_proj_b), nullptr, 0,
+                            cx + ((size_t)b * RC + NL) * D, D, S_mel, D, C, ACT_NONE),
+                       sk, kSplitKFloats, nullptr, st, nl));
+    CK(launch_copy_rows(ctx->w(L.pc_latents), 0, lat, (long)NL * D, B, (long)NL * D, st, nl));  // repeat(latents)
+    for (int i = 0; i < g.pc_depth; ++i) {
+        const PcLayerOff& o = L.pc_layers[i];
+        CK(launch_copy_rows(lat, (long)NL * D, cx, (long)RC * D, B, (long)NL * D, st, nl));  // ctx = [latents ; x]
+        CK(launch_gemm(gemm(lat, D, ctx->w(o.to_q), D, 1, nullptr, nullptr, 0, q, inner, B * NL, inner, D, ACT_NONE), sk,
+                       kSplitKFloats, nullptr, st, nl));
+        CK(launch_gemm(gemm(cx, D, ctx->w(o.to_kv), D, 1, nullptr, nullptr, 0, kvb, 2 * inner, B * RC, 2 * inner, D, ACT_NONE), sk,
+                       kSplitKFloats, nullptr, st, nl));
+        AttnArgs a;
+        a.Q = q;           a.q_bs = (long)NL * inner;     a.q_rs = inner;     a.q_hs = g.pc_dim_head;
+        a.K = kvb;         a.k_bs = (long)RC * 2 * inner; a.k_rs = 2 * inner; a.k_hs = g.pc_dim_head;
+        a.V = kvb + inner; a.v_bs = (long)RC * 2 * inner; a.v_rs = 2 * inner; a.v_hs = g.pc_dim_head;
+        a.O = ob;          a.o_bs = (long)NL * inner;     a.o_rs = inner;     a.o_hs = g.pc_dim_head;
+        a.B = B; a.H = g.pc_heads; a.M = NL; a.hd = g.pc_dim_head; a.n_keys = RC; a.causal = 0; a.pos0 = 0;
+        a.scale = 1.0f / sqrtf((float)g.pc_dim_head);
+        CK(launch_attention(a, nullptr, st, nl));
+        CK(launch_gemm(gemm(ob, inner, ctx->w(o.to_out), inner, 1, nullptr, lat, D, lat, D, B * NL, D, inner, ACT_NONE), sk,
+                       kSplitKFloats, nullptr, st, nl));
+        CK(launch_gemm(gemm(lat, D, ctx->w(o.ff0_w), D, 1, ctx->w(o.ff0_b), nullptr, 0, hb, 2 * ffi, B * NL, 2 * ffi, D, ACT_NONE),
+                       sk, kSplitKFloats, nullptr, st, nl));
+        CK(launch_geglu(hb, B * NL, ffi, ffp, gb, st, nl));
+        CK(launch_gemm(gemm(gb, ffp, ctx->w(o.ff2_w), ffp, 1, ctx->w(o.ff2_b), lat, D, lat, D, B * NL, D, ffp, ACT_NONE), sk,
+                       kSplitKFloats, nullptr, st, nl));
+    }
+    CK(launch_rmsnorm(lat, latents_out_dev, B * NL, D, ctx->w(L.pc_gamma), st, nl));
+    return GENVC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prefix embedding + prefill
+// ---------------------------------------------------------------------------------------------
+int genvc_embed_prefix(genvc_ctx* ctx, const float* cond_dev, const int64_t* text_ids_dev, int B, int T, float* prefix_out_dev,
+                       void* stream) {
+    if (int rc = check_ready(ctx)) return rc;
+    const genvc_config& g = ctx->cfg;
+    if (!cond_dev || !text_ids_dev || !prefix_out_dev) return ctx->fail(GENVC_E_INVALID, "null pointer");
+    if (B <= 0 || T < 0 || T + 2 > g.n_text_pos)
+        return ctx->fail(GENVC_E_INVALID, "text length %d exceeds the %d text positions", T, g.n_text_pos - 2);
+    const Layout& L = ctx->layout;
+    const int P = g.pc_latents + T + 2;
+    CK(launch_embed_prefix(cond_dev, reinterpret_cast<const long long*>(text_ids_dev), B, T, g.pc_latents, g.d_model,
+                           ctx->w(L.text_emb), ctx->w(L.text_pos), g.start_text, g.stop_text, prefix_out_dev, (long)P * g.d_model,
+                           (cudaStream_t)stream, &ctx->nlaunch));
+    return GENVC_OK;
+}
+
+int genvc_prefill(genvc_ctx* ctx, const float* prefix_dev, int B, int P, void* stream) {
+    if (int rc = check_ready(ctx)) return rc;
+    const genvc_config& g = ctx->cfg;
+    if (!prefix_dev) return ctx->fail(GENVC_E_INVALID, "null pointer");
+    if (B <= 0 || B > g.max_batch) return ctx->fail(GENVC_E_INVALID, "batch %d outside [1, %d]", B, g.max_batch);
+    if (P <= 0 || P + 1 + g.max_gen_mel_tokens > g.max_seq)
+        return ctx->fail(GENVC_E_INVALID, "prefix %d + %d generated tokens exceed the KV cache (%d positions)", P,
+                         g.max_gen_mel_tokens, g.max_seq);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout& L = ctx->layout;
+    const int D = g.d_model, M = P + 1;
+    float* X = ctx->at<float>(ctx->o_X);
+    // rows = [prefix (P) ; mel_embedding[start_audio] + mel_pos[0]]   (layers/gpt_inference.py:81-91)
+    CK(launch_copy_rows(prefix_dev, (long)P * D, X, (long)M * D, B, (long)P * D, st, &ctx->nlaunch));
+    CK(launch_embed_mel_rows(nullptr, B, 1, 0, g.start_audio, g.stop_audio, 0, D, ctx->w(L.mel_emb), ctx->w(L.mel_pos),
+                             X + (size_t)P * D, (long)M * D, st, &ctx->nlaunch));
+    if (int rc = run_blocks(ctx, B, M, 0, nullptr, st)) return rc;
+    if (int rc = run_head(ctx, B, M, P, nullptr, st)) return rc;
+    CK(launch_init_state(ctx->at<GenState>(ctx->o_state), ctx->at<unsigned char>(ctx->o_seen), B, P, g.n_audio_vocab, ctx->Vpad,
+                         g.start_audio, st, &ctx->nlaunch));
+    ctx->B = B;
+    ctx->P = P;
+    ctx->prefilled = true;
+    ctx->pending = true;
+    ctx->n_host = 0;
+    return GENVC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode
+// ---------------------------------------------------------------------------------------------
+int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const float* exp_noise_dev, const int64_t* forced_ids_dev,
+                 int64_t* ids_out_dev, float* latents_out_dev, float* logits_out_dev, int32_t* status_dev, int mode, void* stream) {
+    if (int rc = check_ready(ctx)) return rc;
+    if (!ctx->prefilled) return ctx->fail(GENVC_E_STATE, "genvc_decode before genvc_prefill");
+    if (!sp || !ids_out_dev || !latents_out_dev || !status_dev) return ctx->fail(GENVC_E_INVALID, "null pointer");
+    if (n_steps <= 0) return ctx->fail(GENVC_E_INVALID, "n_steps must be positive");
+    if (mode < 0 || mode > 2) return ctx->fail(GENVC_E_INVALID, "mode must be 0, 1 or 2");
+    if (!(sp->temperature > 0.0f) || !(sp->repetition_penalty > 0.0f) || sp->top_k < 0)
+        return ctx->fail(GENVC_E_INVALID, "temperature / repetition_penalty must be > 0 and top_k >= 0");
+    const genvc_config& g = ctx->cfg;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = ctx->B, D = g.d_model, V = g.n_audio_vocab;
+    int max_total = g.max_gen_mel_tokens;
+    if (sp->max_new_tokens > 0) max_total = std::min(max_total, (int)sp->max_new_tokens);
+    const bool can_mega = ctx->mega_ok && ctx->stream_packed && B == 1 && ctx->n_sm == ctx->grid;
+    if (mode == 2 && !can_mega)
+        return ctx->fail(GENVC_E_UNSUPPORTED, "fused decode needs batch 1, a packed decode stream and a supported shape");
+    const bool mega = mode == 2 || (mode == 0 && can_mega);
+    GenState* gs = ctx->at<GenState>(ctx->o_state);
+    unsigned char* seen = ctx->at<unsigned char>(ctx->o_seen);
+    CK(cudaMemsetAsync(status_dev, 0, 2 * sizeof(int32_t), st));
+
+    if (mega) {
+        const Layout& L = ctx->layout;
+        MegaParams p;
+        memset(&p, 0, sizeof p);
+        p.L = g.n_layer; p.D = D; p.H = g.n_head; p.V = V; p.Vpad = ctx->Vpad; p.S_max = g.max_seq;
+        p.P = ctx->P; p.n_steps = n_steps; p.nslot = kMegaSlots;
+        p.stream = ctx->stream; p.blob = ctx->blob;
+        p.ln1_off = (long long)L.layers[0].ln1_w;
+        p.ln2_off = (long long)L.layers[0].ln2_w;
+        p.layer_stride = g.n_layer > 1 ? (long long)(L.layers[1].ln1_w - L.layers[0].ln1_w) : 0;
+        p.lnf_off = (long long)L.lnf_w; p.mel_emb_off = (long long)L.mel_emb; p.mel_pos_off = (long long)L.mel_pos;
+        p.kv = ctx->kv; p.kv_layer_stride = (long long)ctx->kv_plane();
+        p.x = ctx->at<float>(ctx->o_mx); p.qbuf = ctx->at<float>(ctx->o_mq); p.ubuf = ctx->at<float>(ctx->o_mu);
+        p.att_o = ctx->at<float>(ctx->o_matt_o); p.att_ml = ctx->at<float>(ctx->o_matt_ml);
+        p.pend_logits = ctx->at<float>(ctx->o_pend_logits); p.pend_latent = ctx->at<float>(ctx->o_pend_latent);
+        p.st = gs; p.seen = seen; p.barrier = ctx->at<unsigned>(ctx->o_barrier);
+        p.top_k = sp->top_k; p.top_p = sp->top_p; p.top_p_threshold = sp->top_p_threshold; p.temperature = sp->temperature;
+        p.rep_penalty = sp->repetition_penalty; p.ignore_eos = sp->ignore_eos; p.stop_token = g.stop_audio;
+        p.max_total = max_total; p.seed = sp->seed;
+        p.noise = exp_noise_dev; p.forced = reinterpret_cast<const long long*>(forced_ids_dev);
+        p.ids_out = reinterpret_cast<long long*>(ids_out_dev); p.latents_out = latents_out_dev; p.logits_out = logits_out_dev;
+        p.status = status_dev;
+        CK(launch_decode_mega(p, ctx->grid, st));
+        ctx->nlaunch += 1;
+        ctx->n_host = std::min(max_total, ctx->n_host + n_steps);
+        ctx->pending = false;
+        return GENVC_OK;
+    }
+
+    // per-op path (any batch): one forward + one sample kernel per step; steps enqueued after the
+    // device-side loop has finished are skipped on the device (GenState::done)
+    const Layout& L = ctx->layout;
+    const int* skip = &gs->done;
+    for (int i = 0; i < n_steps; ++i) {
+        const int n = ctx->n_host;
+        if (n >= max_total) break;
+        if (!ctx->pending) {
+            // forward of the last token at mel position n, cache row P + n   (layers/gpt_inference.py:92-96)
+            CK(launch_embed_last_token(gs, B, n, D, ctx->w(L.mel_emb), ctx->w(L.mel_pos), ctx->at<float>(ctx->o_X), st, &ctx->nlaunch));
+            if (int rc = run_blocks(ctx, B, 1, ctx->P + n, skip, st)) return rc;
+            if (int rc = run_head(ctx, B, 1, 0, skip, st)) return rc;
+        }
+        SampleArgs a;
+        memset(&a, 0, sizeof a);
+        a.st = gs; a.logits = ctx->at<float>(ctx->o_pend_logits); a.latent = ctx->at<float>(ctx->o_pend_latent); a.seen = seen;
+        a.V = V; a.Vpad = ctx->Vpad; a.D = D;
+        a.top_k = sp->top_k; a.top_p = sp->top_p; a.top_p_threshold = sp->top_p_threshold; a.temperature = sp->temperature;
+        a.rep_penalty = sp->repetition_penalty; a.ignore_eos = sp->ignore_eos; a.stop_token = g.stop_audio; a.max_total = max_total;
+        a.seed = sp->seed;
+        a.noise = exp_noise_dev ? exp_noise_dev + (size_t)i * B * V : nullptr;
+        a.forced = forced_ids_dev ? reinterpret_cast<const long long*>(forced_ids_dev) + (size_t)i * B : nullptr;
+        a.ids_out = reinterpret_cast<long long*>(ids_out_dev) + (size_t)i * B;
+        a.latents_out = latents_out_dev + (size_t)i * B * D;
+        a.logits_out = logits_out_dev ? logits_out_dev + (size_t)i * B * V : nullptr;
+        a.status = status_dev; a.step_in_call = i;
+        CK(launch_sample(a, B, st, &ctx->nlaunch));
+        ctx->n_host = n + 1;
+        ctx->pending = false;
+    }
+    return GENVC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// teacher-forced latent pass
+// ---------------------------------------------------------------------------------------------
+int genvc_forward_latents(genvc_ctx* ctx, const float* cond_dev, const int64_t* text_ids_dev, int T, const int64_t* codes_dev,
+                          int M, int B, float* latents_out_dev, void* stream) {
+    if (int rc = check_ready(ctx)) return rc;
+    const genvc_config& g = ctx->cfg;
+    if (!cond_dev || !text_ids_dev || !codes_dev || !latents_out_dev) return ctx->fail(GENVC_E_INVALID, "null pointer");
+    const int NLp = g.pc_latents, D = g.d_model;
+    const int RT = T + 2, RM = M + 5, R = NLp + RT + RM;
+    if (B <= 0 || M <= 0 || T < 0) return ctx->fail(GENVC_E_INVALID, "bad B/T/M");
+    if (RT > g.n_text_pos || RM > g.n_mel_pos) return ctx->fail(GENVC_E_INVALID, "sequence exceeds the position tables");
+    if ((size_t)B * R > ctx->rows_cap()) return ctx->fail(GENVC_E_INVALID, "B*rows = %d exceeds the workspace (%zu rows)", B * R, ctx->rows_cap());
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout& L = ctx->layout;
+    float* X = ctx->at<float>(ctx->o_X);
+    // rows = [cond (32) ; text (T+2) ; start, codes, stop x4 (M+5)]
+    CK(launch_embed_prefix(cond_dev, reinterpret_cast<const long long*>(text_ids_dev), B, T, NLp, D, ctx->w(L.text_emb),
+                           ctx->w(L.text_pos), g.start_text, g.stop_text, X, (long)R * D, st, &ctx->nlaunch));
+    CK(launch_embed_mel_rows(reinterpret_cast<const long long*>(codes_dev), B, RM, M, g.start_audio, g.stop_audio, 0, D,
+                             ctx->w(L.mel_emb), ctx->w(L.mel_pos), X + (size_t)(NLp + RT) * D, (long)R * D, st, &ctx->nlaunch));
+    if (int rc = run_blocks(ctx, B, R, -1, nullptr, st)) return rc;
+    // final_norm(ln_f(h)) of the first M mel rows of each element
+    CK(launch_layernorm(X + (size_t)(NLp + RT) * D, D, (long)R * D, latents_out_dev, D, (long)M * D, B * M, M, D, ctx->w(L.lnf_w),
+                        ctx->w(L.lnf_b), ctx->w(L.fn_w), ctx->w(L.fn_b), nullptr, st, &ctx->nlaunch));
+    // this pass reuses the row buffers but not the KV cache or the generation state
+    return GENVC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// KV-cache attention microbenchmark
+// ---------------------------------------------------------------------------------------------
+int genvc_kv_attention(const float* q_dev, const float* k_dev, const float* v_dev, int N, int H, int hd, int S, int S_max,
+                       float* out_dev, void* stream) {
+    if (!q_dev || !k_dev || !v_dev || !out_dev || N <= 0 || H <= 0 || !valid_hd(hd) || S <= 0 || S > S_max) return GENVC_E_INVALID;
+    cudaError_t e = launch_kv_attention(q_dev, (long)H * hd, k_dev, v_dev, (long)H * S_max * hd, N, H, hd, S, S_max, out_dev,
+                                        (long)H * hd, nullptr, (cudaStream_t)stream, nullptr);
+    return e == cudaSuccess ? GENVC_OK : GENVC_E_CUDA;
+}
+
+}  // extern "C"

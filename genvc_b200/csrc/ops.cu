@@ -582,7 +582,6 @@ __global__ void __launch_bounds__(GV_SAMPLE_THREADS) sample_kernel(SampleArgs a,
     __shared__ unsigned long long keys[GV_SORT_N];
     __shared__ float fscr[16];
     __shared__ int iscr[16];
-    __shared__ int s_tok;
     const int b = blockIdx.x, tid = threadIdx.x;
     const float* lg = a.logits + (size_t)b * a.V;
     unsigned char* seen = a.seen + (size_t)b * a.Vpad;
@@ -593,7 +592,6 @@ __global__ void __launch_bounds__(GV_SAMPLE_THREADS) sample_kernel(SampleArgs a,
     if (a.forced) tok = (int)a.forced[b];
     const int was_finished = st->finished[b];
     if (!a.ignore_eos && was_finished) tok = a.stop_token;  // finished rows emit the pad (== eos) token
-    if (tid == 0) s_tok = tok;
     // emit (token, latent[, logits]) — the yield of sample_stream happens before the EOS test
     if (tid == 0) a.ids_out[b] = tok;
     for (int i = tid; i < a.D; i += blockDim.x) a.latents_out[(size_t)b * a.D + i] = ldcg(a.latent + (size_t)b * a.D + i);
@@ -630,29 +628,36 @@ cudaError_t launch_sample(const SampleArgs& a, int B, cudaStream_t st, unsigned 
 }
 
 // =============================================================================================
-// KV-cache attention microbenchmark (BASELINE configs[4]): one CTA per (cache, head)
+// Single-query KV-cache attention: one CTA (8 warps) per (cache row b, head h).  Used by the
+// batched per-op decode step and by the KV microbenchmark (BASELINE configs[4]).
+//   q   + b*q_bs + h*HD          k,v + b*kv_bs + h*S_max*HD          out + b*o_bs + h*HD
 // =============================================================================================
 template <int HD>
-__global__ void __launch_bounds__(256) kv_attention_bench_kernel(const float* __restrict__ q, const float* __restrict__ k,
-                                                                 const float* __restrict__ v, int H, int S, int S_max,
-                                                                 float* __restrict__ out) {
+__global__ void __launch_bounds__(256) kv_attention_kernel(const float* __restrict__ q, long q_bs,
+                                                           const float* __restrict__ k, const float* __restrict__ v,
+                                                           long kv_bs, int S, int S_max, float* __restrict__ out, long o_bs,
+                                                           const int* skip) {
+    if (skip && *skip) return;
     __shared__ float sm[GV_ATT_WARPS * (HD + 2)];
-    const size_t item = blockIdx.x;  // n * H + h
-    const float* Kc = k + item * (size_t)S_max * HD;
-    const float* Vc = v + item * (size_t)S_max * HD;
-    attn_decode_item<HD>(q + item * HD, Kc, Vc, 0, S, sqrtf((float)HD), sm, threadIdx.x, BlockSync(), out + item * HD,
-                         nullptr);
+    const size_t b = blockIdx.y, h = blockIdx.x;
+    const float* Kc = k + b * kv_bs + h * (size_t)S_max * HD;
+    const float* Vc = v + b * kv_bs + h * (size_t)S_max * HD;
+    attn_decode_item<HD>(q + b * q_bs + h * HD, Kc, Vc, 0, S, sqrtf((float)HD), sm, threadIdx.x, BlockSync(),
+                         out + b * o_bs + h * HD, nullptr);
 }
-cudaError_t launch_kv_attention_bench(const float* q, const float* k, const float* v, int N, int H, int hd, int S, int S_max,
-                                      float* out, cudaStream_t st) {
-    dim3 grid(N * H);
+cudaError_t launch_kv_attention(const float* q, long q_bs, const float* k, const float* v, long kv_bs, int B, int H, int hd,
+                                int S, int S_max, float* out, long o_bs, const int* skip, cudaStream_t st,
+                                unsigned long long* nlaunch) {
+    if (B <= 0 || H <= 0 || S <= 0 || S > S_max) return cudaErrorInvalidValue;
+    dim3 grid(H, B);
     switch (hd) {
-        case 32: kv_attention_bench_kernel<32><<<grid, 256, 0, st>>>(q, k, v, H, S, S_max, out); break;
-        case 64: kv_attention_bench_kernel<64><<<grid, 256, 0, st>>>(q, k, v, H, S, S_max, out); break;
-        case 128: kv_attention_bench_kernel<128><<<grid, 256, 0, st>>>(q, k, v, H, S, S_max, out); break;
-        case 256: kv_attention_bench_kernel<256><<<grid, 256, 0, st>>>(q, k, v, H, S, S_max, out); break;
+#define GV_KVA_CASE(n) \
+    case n: kv_attention_kernel<n><<<grid, 256, 0, st>>>(q, q_bs, k, v, kv_bs, S, S_max, out, o_bs, skip); break;
+        GV_KVA_CASE(32) GV_KVA_CASE(64) GV_KVA_CASE(128) GV_KVA_CASE(256)
+#undef GV_KVA_CASE
         default: return cudaErrorInvalidValue;
     }
+    GV_BUMP(nlaunch);
     return cudaGetLastError();
 }
 

@@ -101,7 +101,8 @@ cudaError_t launch_geglu(const float* h, int rows, int inner, int inner_pad, flo
 cudaError_t launch_init_state(GenState* st, unsigned char* seen, int B, int P, int V, int Vpad, int start_audio,
                               cudaStream_t s, unsigned long long* nlaunch);
 cudaError_t launch_sample(const SampleArgs& a, int B, cudaStream_t st, unsigned long long* nlaunch);
-cudaError_t launch_kv_attention_bench(const float* q, const float* k, const float* v, int N, int H, int hd, int S, int S_max,
-                                      float* out, cudaStream_t st);
+cudaError_t launch_kv_attention(const float* q, long q_bs, const float* k, const float* v, long kv_bs, int B, int H, int hd,
+                                int S, int S_max, float* out, long o_bs, const int* skip, cudaStream_t st,
+                                unsigned long long* nlaunch);
 
 }  // namespace gv

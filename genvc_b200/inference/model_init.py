@@ -1,0 +1,102 @@
+"""``model_init(checkpoint_path, device) -> (model, config)`` with the reference's contract
+(``inference/model_init.py:9-34``) for the codec-token path.
+
+The checkpoint layout is the reference's: ``torch.load(path)`` -> ``{"config": nested dict,
+"model": flat state_dict}``; the GPT's tensors live under the ``gpt.`` prefix and are loaded
+non-strictly (everything else in the file — DVAEs, HiFi-GAN, discriminators — is ignored here).
+``config`` is returned as a mutable attribute-dict so ``model.config.top_k = ...`` (``infer.py:22``)
+keeps working without coqpit.
+
+Stages outside this path (ContentVec, content-DVAE, mel front-end, HiFi-GAN; SURVEY.md §2 #9-#11,
+#16) are *attachment points* on the returned model: assign the reference's own modules to
+``model.content_extractor``, ``model.content_dvae``, ``model.hifigan`` and
+``model.torch_mel_spectrogram_style_encoder`` to run the full pipeline.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ..config import GenVCDims, wrap_config
+from ..gpt import GPT
+
+
+class _Unattached:
+    def __init__(self, name: str):
+        self._name = name
+
+    def __getattr__(self, item):
+        raise RuntimeError(
+            f"model.{self._name} is outside the genvc_b200 path and has not been attached; assign the "
+            f"reference module to model.{self._name} (see INTEGRATION.md)"
+        )
+
+    def __call__(self, *a, **k):
+        self.__getattr__("__call__")
+
+
+class GenVCModel:
+    """The slice of ``trainers/hifigan_trainer.py::HiFiGANTrainer`` the inference drivers touch."""
+
+    def __init__(self, config, device, max_batch: int = 1, max_mel_frames: int = 576):
+        self.config = config
+        self.dims = GenVCDims.from_config(config)
+        self.device = torch.device(device)
+        self.gpt = GPT(self.dims, device=device, max_batch=max_batch, max_mel_frames=max_mel_frames)
+        # trainers/hifigan_trainer.py:62-66, 93-95: 24 kHz output / (1024-sample code stride / 4x latent upsampling)
+        self.content_sample_rate = 16000
+        self.hifigan_scale_factor = 4
+        self.content_extractor = _Unattached("content_extractor")
+        self.content_dvae = _Unattached("content_dvae")
+        self.hifigan = _Unattached("hifigan")
+        self.torch_mel_spectrogram_style_encoder = _Unattached("torch_mel_spectrogram_style_encoder")
+
+    def load_state_dict(self, state_dict, strict: bool = False):
+        self.gpt.load_state_dict(state_dict, strict=strict)
+        return self
+
+    @torch.inference_mode()
+    def get_gpt_cond_latents(self, audio: torch.Tensor, sr: int, length: int = 30, chunk_length: int = 6) -> torch.Tensor:
+        """Reference audio [1, samples] -> speaker latents [1, 32, D]: clip to ``length`` s, one perceiver
+        pass per ``chunk_length``-s chunk (chunks under 0.33 s dropped), mean over chunks
+        (``trainers/hifigan_trainer.py:438-455``)."""
+        audio = audio[:, : sr * length]
+        mels = []
+        for i in range(0, audio.shape[1], sr * chunk_length):
+            chunk = audio[:, i: i + sr * chunk_length]
+            if chunk.size(-1) < sr * 0.33:
+                continue
+            mels.append(self.torch_mel_spectrogram_style_encoder(chunk.unsqueeze(0)))
+        return self.get_gpt_cond_latents_from_mels(mels)
+
+    @torch.inference_mode()
+    def get_gpt_cond_latents_from_mels(self, mel_chunks) -> torch.Tensor:
+        """Same, entered after the mel front-end: list of [B, 80, S_i] (or [B, 1, 80, S_i])."""
+        if not mel_chunks:
+            raise ValueError("no reference chunk of at least 0.33 s")
+        embs = [self.gpt.get_style_emb(m.to(self.device), None) for m in mel_chunks]
+        return torch.stack(embs).mean(dim=0).transpose(1, 2)
+
+
+@torch.inference_mode()
+def model_init(checkpoint_path, device, max_batch: int = 1, max_mel_frames: int = 576):
+    ckpt_states = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+    return model_from_checkpoint(ckpt_states, device, max_batch=max_batch, max_mel_frames=max_mel_frames)
+
+
+def model_from_checkpoint(ckpt_states: dict, device, max_batch: int = 1, max_mel_frames: int = 576,
+                          blob: Optional[torch.Tensor] = None):
+    """``blob``: an already packed weight blob (ranks > 0 receive it by NCCL broadcast instead of
+    re-reading the checkpoint; see ``genvc_b200.replicas``)."""
+    config = wrap_config(ckpt_states["config"])
+    config.is_inference = True
+    model = GenVCModel(config, device, max_batch=max_batch, max_mel_frames=max_mel_frames)
+    if blob is not None:
+        model.gpt.load_blob(blob)
+    else:
+        model.load_state_dict(ckpt_states["model"], strict=False)
+    model.gpt.eval()
+    model.gpt.to(device)
+    model.gpt.init_gpt_for_inference()
+    return model, config

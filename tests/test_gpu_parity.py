@@ -1,0 +1,226 @@
+"""GPU parity: the CUDA path (through the C ABI, via the drop-in ``GPT`` object) against
+(a) the committed golden fixtures the REAL reference generated and (b) the CPU oracle on
+the same seeded inputs.
+
+Bars: token ids bit-exact; teacher-forced logits within 1e-3 abs + 1e-4 rel;
+latents within 1e-4 abs + 1e-4 rel (two fp32 evaluations with different summation orders;
+observed ~1e-5).
+"""
+import pytest
+import torch
+
+from conftest import golden_checkpoint, load_golden
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_ATOL, LOGIT_RTOL = 1e-3, 1e-4
+LAT_ATOL, LAT_RTOL = 1e-4, 1e-4
+TOY = ["toy_d128_greedy", "toy_d128_topk20", "toy_d128_topk0_topp1", "toy_d128_eos", "toy_d256_h4_greedy",
+       "toy_d512_h2_greedy"]
+FULL = ["full_h4_cfg1", "full_h16_greedy", "full_h4_topk20"]
+
+_GPT_CACHE = {}
+
+
+def make_gpt(fx, device, max_batch=1):
+    from genvc_b200.config import GenVCDims
+    from genvc_b200.gpt import GPT
+
+    key = (tuple(sorted(fx["model"].items())), max_batch)
+    if key not in _GPT_CACHE:
+        if len(_GPT_CACHE) >= 2:
+            _GPT_CACHE.clear()
+            torch.cuda.empty_cache()
+        ck = golden_checkpoint(fx)
+        g = GPT(GenVCDims.from_config(ck["config"]), device=device, max_batch=max_batch)
+        g.load_state_dict(ck["model"])
+        g.eval().to(device).init_gpt_for_inference()
+        _GPT_CACHE[key] = g
+    return _GPT_CACHE[key]
+
+
+def fixture_noise(fx, V=1026):
+    if fx["noise_seed"] is None:
+        return None
+    cap = fx["new_tokens"] if fx["new_tokens"] is not None else 602
+    g = torch.Generator().manual_seed(fx["noise_seed"])
+    return torch.empty((cap, fx["ids"].shape[0], V)).exponential_(1, generator=g)
+
+
+def close(a, b, atol, rtol):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    err = (a - b).abs()
+    ok = bool((err <= atol + rtol * b.abs()).all())
+    return ok, float(err.max())
+
+
+def gen_kwargs(fx, **extra):
+    s = fx["sampling"]
+    kw = dict(do_sample=True, top_p=s["top_p"], top_k=s["top_k"], temperature=s["temperature"], num_beams=1,
+              length_penalty=1.0, repetition_penalty=s["repetition_penalty"], output_attentions=False)
+    if fx["new_tokens"] is not None:
+        kw["max_new_tokens"] = fx["new_tokens"]
+    kw.update(extra)
+    return kw
+
+
+# ------------------------------------------------------------------------------------ perceiver
+@pytest.mark.parametrize("name", TOY + FULL)
+def test_perceiver_matches_reference_fixture(name, cuda_device):
+    fx = load_golden(name)
+    g = make_gpt(fx, cuda_device)
+    out = g.get_style_emb(fx["mel"].to(cuda_device))
+    assert out.shape == fx["style_emb"].shape
+    ok, err = close(out, fx["style_emb"], 2e-4, 1e-4)
+    assert ok, f"perceiver max err {err}"
+    out4 = g.get_style_emb(fx["mel"].unsqueeze(1).to(cuda_device))
+    assert torch.equal(out4, out)
+
+
+# ------------------------------------------------------------------------------------ generation
+def _run_generate(fx, g, device, mode):
+    cond = fx["style_emb"].transpose(1, 2).contiguous().to(device)
+    noise = fixture_noise(fx)
+    kw = gen_kwargs(fx, decode_mode=mode)
+    if noise is not None:
+        kw["exp_noise"] = noise.to(device)
+    ids = g.generate(cond, fx["codes"].to(device), **kw)
+    return ids, g.last_latents
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["per_op", "fused"])
+@pytest.mark.parametrize("name", TOY)
+def test_toy_token_ids_bit_exact(name, mode, cuda_device):
+    fx = load_golden(name)
+    g = make_gpt(fx, cuda_device)
+    ids, lats = _run_generate(fx, g, cuda_device, mode)
+    assert ids.dtype == torch.int64
+    assert torch.equal(ids.cpu(), fx["ids"]), f"first mismatch at {(ids.cpu() != fx['ids']).nonzero()[:1].tolist()}"
+    ok, err = close(lats[:, fx["steps"].to(lats.device)], fx["latents"], LAT_ATOL, LAT_RTOL)
+    assert ok, f"latent max err {err}"
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["per_op", "fused"])
+@pytest.mark.parametrize("name", TOY + FULL)
+def test_teacher_forced_logits(name, mode, cuda_device):
+    """Logits of every step with the reference's tokens forced: isolates numerics from sampling."""
+    fx = load_golden(name)
+    n = min(fx["ids"].shape[1], 96 if name in FULL else 10 ** 6)
+    g = make_gpt(fx, cuda_device)
+    eng = g.engine
+    cond = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device)
+    g.compute_embeddings(cond, fx["codes"].to(cuda_device))
+    eng.prefill(g._prefix)
+    from genvc_b200.engine import Sampling
+
+    sp = Sampling(**fx["sampling"], max_new_tokens=n)
+    forced = fx["ids"][:, :n].transpose(0, 1).contiguous().to(cuda_device)
+    ch = eng.decode(n, sp, forced=forced, want_logits=True, mode=mode)
+    emitted, _ = ch.status.tolist()
+    assert emitted == n
+    assert torch.equal(ch.ids.cpu(), forced.cpu())
+    steps = fx["steps"][fx["steps"] < n]
+    got = ch.logits.transpose(0, 1)[:, steps.to(cuda_device)]
+    ok, err = close(got, fx["logits"][:, : len(steps)], LOGIT_ATOL, LOGIT_RTOL)
+    assert ok, f"logit max err {err}"
+    ok, err = close(ch.latents.transpose(0, 1)[:, steps.to(cuda_device)], fx["latents"][:, : len(steps)], LAT_ATOL, LAT_RTOL)
+    assert ok, f"latent max err {err}"
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_full_size_token_ids_bit_exact(name, cuda_device):
+    """BASELINE configs[0] and friends at L=30, D=1024: free-running ids through the fused kernel."""
+    fx = load_golden(name)
+    g = make_gpt(fx, cuda_device)
+    ids, _ = _run_generate(fx, g, cuda_device, 2)
+    assert ids.shape == fx["ids"].shape
+    assert torch.equal(ids.cpu(), fx["ids"]), f"first mismatch at {(ids.cpu() != fx['ids']).nonzero()[:1].tolist()}"
+
+
+def test_full_size_per_op_prefix_matches(cuda_device):
+    fx = load_golden("full_h4_cfg1")
+    g = make_gpt(fx, cuda_device)
+    cond = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device)
+    ids = g.generate(cond, fx["codes"].to(cuda_device), **gen_kwargs(fx, decode_mode=1, max_new_tokens=40))
+    assert torch.equal(ids.cpu(), fx["ids"][:, :40])
+
+
+def test_batched_rows_equal_reference(cuda_device):
+    """A7: equal-T batch through the per-op path; rows finish at different steps and are padded with 1025."""
+    fx = load_golden("toy_d128_batch3")
+    g = make_gpt(fx, cuda_device, max_batch=3)
+    out = g.get_style_emb(fx["mel"].to(cuda_device))
+    ok, err = close(out, fx["style_emb"], 2e-4, 1e-4)
+    assert ok, err
+    ids, lats = _run_generate(fx, g, cuda_device, 0)
+    assert torch.equal(ids.cpu(), fx["ids"])
+    ok, err = close(lats[:, fx["steps"].to(lats.device)], fx["latents"], LAT_ATOL, LAT_RTOL)
+    assert ok, f"latent max err {err}"
+
+
+# ------------------------------------------------------------------------------------ latent pass
+@pytest.mark.parametrize("name", ["toy_d128_greedy", "toy_d256_h4_greedy", "toy_d128_eos", "full_h4_cfg1"])
+def test_latent_pass(name, cuda_device):
+    fx = load_golden(name)
+    g = make_gpt(fx, cuda_device)
+    cond = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device)[:1]
+    g0 = fx["ids"][0][fx["ids"][0] != 1025]
+    codes = fx["codes"][:1].to(cuda_device)
+    lat = g(codes, torch.tensor([codes.shape[1]]), g0[None].to(cuda_device), torch.tensor([g0.numel() * 1024]),
+            cond_latents=cond, return_latent=True)
+    assert lat.shape == (1, g0.numel(), g.model_dim)
+    if fx["latent_pass_steps"] is not None:
+        lat = lat[:, fx["latent_pass_steps"].to(cuda_device)]
+    ok, err = close(lat, fx["latent_pass"], LAT_ATOL, LAT_RTOL)
+    assert ok, f"latent-pass max err {err}"
+
+
+# ------------------------------------------------------------------------------------ streaming protocol
+@pytest.mark.parametrize("name,chunk", [("toy_d128_eos", 8), ("toy_d128_greedy", 5), ("toy_d128_topk20", 8)])
+def test_streaming_generator_protocol(name, chunk, cuda_device):
+    """(token, latent) per step, EOS pair delivered, StopIteration afterwards; ids equal generate()'s."""
+    fx = load_golden(name)
+    g = make_gpt(fx, cuda_device)
+    cond = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device)
+    fake = g.compute_embeddings(cond, fx["codes"].to(cuda_device))
+    P = 32 + fx["codes"].shape[1] + 2
+    assert fake.shape == (1, P + 1) and fake.dtype == torch.int64
+    assert fake[0, :-1].eq(1).all() and fake[0, -1].item() == 1024
+    kw = gen_kwargs(fx, num_return_sequences=1, output_hidden_states=True, stream_chunk_size=chunk)
+    noise = fixture_noise(fx)
+    if noise is not None:
+        kw["exp_noise"] = noise.to(cuda_device)
+    gen = g.get_generator(fake_inputs=fake, **kw)
+    toks, lats = [], []
+    while True:
+        try:
+            x, latent = next(gen)
+        except StopIteration:
+            break
+        assert x.shape == (1,) and x.dtype == torch.int64
+        assert latent.shape == (1, g.model_dim) and latent.dtype == torch.float32
+        toks.append(x)
+        lats.append(latent)
+    ids = torch.stack(toks, 1).cpu()
+    assert torch.equal(ids, fx["ids"])
+    if name == "toy_d128_eos":
+        assert ids[0, -1].item() == 1025  # the EOS step's pair is delivered
+    ok, err = close(torch.stack(lats, 1)[:, fx["steps"].to(cuda_device)], fx["latents"], LAT_ATOL, LAT_RTOL)
+    assert ok, err
+
+
+def test_philox_sampling_is_seed_reproducible(cuda_device):
+    fx = load_golden("toy_d128_topk20")
+    g = make_gpt(fx, cuda_device)
+    cond = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device)
+    codes = fx["codes"].to(cuda_device)
+    kw = gen_kwargs(fx)
+    torch.manual_seed(5)
+    a = g.generate(cond, codes, **kw)
+    torch.manual_seed(5)
+    b = g.generate(cond, codes, **kw)
+    torch.manual_seed(6)
+    c = g.generate(cond, codes, **kw)
+    assert torch.equal(a, b)
+    assert not torch.equal(a, c)
+    assert (a >= 0).all() and (a < 1026).all()
