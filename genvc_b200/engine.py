@@ -16,9 +16,8 @@ import numpy as np
 import torch
 
 from .config import GenVCDims
-from .lib import GenvcConfig, GenvcError, GenvcSampling, load_library
-
-PREFIX = "gpt."  # state-dict prefix of the GPT inside a GenVC checkpoint (trainers/hifigan_trainer.py:31)
+from .lib import GenvcError, GenvcSampling, load_library
+from .weights import c_config, pack_state_dict, tensor_table
 
 
 @dataclass
@@ -77,16 +76,7 @@ class Engine:
         if max_seq is None:
             max_seq = (dims.max_seq + 7) // 8 * 8
         self.max_batch, self.max_seq, self.max_mel_frames = int(max_batch), int(max_seq), int(max_mel_frames)
-        self.cfg = GenvcConfig(
-            n_layer=dims.n_layer, d_model=dims.d_model, n_head=dims.n_head,
-            n_text_vocab=dims.n_text_vocab, n_audio_vocab=dims.n_audio_vocab,
-            start_text=dims.start_text, stop_text=dims.stop_text,
-            start_audio=dims.start_audio, stop_audio=dims.stop_audio,
-            n_mel_pos=dims.n_mel_pos, n_text_pos=dims.n_text_pos, max_gen_mel_tokens=dims.max_gen_mel_tokens,
-            pc_depth=dims.pc_depth, pc_dim_context=dims.pc_dim_context, pc_latents=dims.pc_latents,
-            pc_dim_head=dims.pc_dim_head, pc_heads=dims.pc_heads, pc_ff_inner=dims.pc_ff_inner,
-            max_batch=self.max_batch, max_seq=self.max_seq, max_mel_frames=self.max_mel_frames,
-        )
+        self.cfg = c_config(dims, self.max_batch, self.max_seq, self.max_mel_frames)
         self._ctx = C.c_void_p()
         rc = self.lib.genvc_create(C.byref(self.cfg), self.dev_index, C.byref(self._ctx))
         if rc != 0:
@@ -104,7 +94,11 @@ class Engine:
                                                 self.ws.numel()))
         self._B = 0
         self._P = 0
+        self._pending = False  # logits of the next step already computed (by prefill)
+        self._n = 0  # host mirror of the number of tokens emitted since prefill (upper bound)
         self.validate_device_ids = True
+        # bench hook: when a list, every decode() appends (start_event, end_event, n_forward, first_S)
+        self.timing: Optional[list] = None
 
     # ------------------------------------------------------------------ plumbing
     def __del__(self):
@@ -152,42 +146,14 @@ class Engine:
 
     # ------------------------------------------------------------------ weights
     def tensor_table(self) -> List[Tuple[str, int, int, int, int]]:
-        """(key, float offset, rows, cols, row stride) of every tensor of the blob."""
-        out = []
-        buf = C.create_string_buffer(256)
-        o, r, c, s = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
-        for i in range(self.lib.genvc_num_tensors(self._ctx)):
-            self._check(self.lib.genvc_tensor_name(self._ctx, i, buf, 256))
-            self._check(self.lib.genvc_tensor_info(self._ctx, buf.value, C.byref(o), C.byref(r), C.byref(c), C.byref(s)))
-            out.append((buf.value.decode(), o.value, r.value, c.value, s.value))
-        return out
+        return tensor_table(self.lib, self._ctx)
 
     @property
     def blob_floats(self) -> int:
         return int(self.lib.genvc_blob_floats(self._ctx))
 
-    def pack_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True) -> torch.Tensor:
-        """Host-side packing of the checkpoint's ``gpt.*`` tensors into one fp32 blob
-        (replaces ``model.load_state_dict`` for this path, inference/model_init.py:22)."""
-        blob = torch.zeros(self.blob_floats, dtype=torch.float32)
-        missing = []
-        for key, off, rows, cols, stride in self.tensor_table():
-            t = state_dict.get(PREFIX + key)
-            if t is None:
-                if key.startswith("text_head."):  # unused at inference; tolerate pruned checkpoints
-                    continue
-                missing.append(PREFIX + key)
-                continue
-            t = t.detach().to(torch.float32).reshape(rows, cols) if t.numel() == rows * cols else None
-            if t is None:
-                raise ValueError(f"checkpoint tensor {PREFIX + key} has the wrong shape (want {rows}x{cols})")
-            blob[off: off + rows * stride].view(rows, stride)[:, :cols].copy_(t)
-        if missing and strict:
-            raise KeyError(f"checkpoint is missing {len(missing)} tensors, e.g. {missing[:3]}")
-        return blob
-
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
-        self.load_blob(self.pack_state_dict(state_dict, strict))
+        self.load_blob(pack_state_dict(self.dims, state_dict, strict))
 
     def load_blob(self, blob: torch.Tensor):
         """Bind a packed blob (host or device tensor) and build the decode weight stream."""
@@ -234,6 +200,7 @@ class Engine:
         B, P, _ = prefix.shape
         self._check(self.lib.genvc_prefill(self._ctx, prefix.data_ptr(), B, P, self._stream()))
         self._B, self._P = B, P
+        self._pending, self._n = True, 0
         self._keep = prefix  # stays alive until the stream has consumed it
 
     def decode(self, n_steps: int, sampling: Sampling, noise: Optional[torch.Tensor] = None,
@@ -256,8 +223,21 @@ class Engine:
         lg = torch.zeros((n_steps, B, V), dtype=torch.float32, device=dev) if want_logits else None
         status = torch.zeros(2, dtype=torch.int32, device=dev)
         sp = sampling.to_c()
+        ev = None
+        if self.timing is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream(self.device))
         self._check(self.lib.genvc_decode(self._ctx, n_steps, C.byref(sp), _ptr(noise), _ptr(forced), ids.data_ptr(),
                                           lat.data_ptr(), _ptr(lg), status.data_ptr(), mode, self._stream()))
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(self.device))
+            # forwards in this call (the first step after prefill samples from the prefill's logits) and
+            # the number of keys the first of them attends
+            n_fwd = n_steps - (1 if self._pending else 0)
+            first_S = self._P + self._n + (1 if self._pending else 0) + 1
+            self.timing.append((ev[0], ev[1], n_fwd, first_S))
+        self._pending = False
+        self._n += n_steps
         self._keep2 = (noise, forced)
         return DecodeChunk(ids, lat, lg, status)
 
