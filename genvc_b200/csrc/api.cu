@@ -60,6 +60,10 @@ struct genvc_ctx {
     size_t ws_bytes = 0;
     int Vpad = 0;
 
+    // debug timeline of the fused decode kernel (genvc_debug_trace)
+    unsigned long long* trace = nullptr;
+    int trace_slots = 0, trace_step = 0;
+
     // host mirror of the generation state
     int B = 0, P = 0;
     bool prefilled = false, pending = false;
@@ -267,6 +271,15 @@ int genvc_bind_buffers(genvc_ctx* ctx, float* kv_dev, uint64_t kv_floats, void* 
 }
 
 uint64_t genvc_launch_count(const genvc_ctx* ctx) { return ctx ? ctx->nlaunch : 0; }
+
+int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, int step) {
+    if (!ctx) return GENVC_E_INVALID;
+    if (trace_dev && (slots_per_cta <= 0 || step < 0)) return ctx->fail(GENVC_E_INVALID, "bad trace geometry");
+    ctx->trace = reinterpret_cast<unsigned long long*>(trace_dev);
+    ctx->trace_slots = trace_dev ? slots_per_cta : 0;
+    ctx->trace_step = step;
+    return GENVC_OK;
+}
 
 }  // extern "C"
 
@@ -506,6 +519,7 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         p.noise = exp_noise_dev; p.forced = reinterpret_cast<const long long*>(forced_ids_dev);
         p.ids_out = reinterpret_cast<long long*>(ids_out_dev); p.latents_out = latents_out_dev; p.logits_out = logits_out_dev;
         p.status = status_dev;
+        p.trace = ctx->trace; p.trace_slots = ctx->trace_slots; p.trace_step = ctx->trace_step;
         CK(launch_decode_mega(p, ctx->grid, st));
         ctx->nlaunch += 1;
         ctx->n_host = std::min(max_total, ctx->n_host + n_steps);

@@ -128,6 +128,12 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (on-device sampling noise when the host supplies none)
 // ---------------------------------------------------------------------------------------------

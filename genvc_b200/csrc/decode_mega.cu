@@ -364,6 +364,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
         const float* mel_pos = p.blob + p.mel_pos_off;
 
         for (int i = 0; i < p.n_steps; ++i) {
+            const bool tr = p.trace != nullptr && i == p.trace_step && tid == 0;
+            unsigned long long* trow = p.trace + (size_t)cta * p.trace_slots;
+            auto stamp = [&](int slot) {
+                if (tr && slot < p.trace_slots) trow[slot] = globaltimer_ns();
+            };
+            stamp(p.L * 10 + 3);
             if (!(i == 0 && had_pending)) {
                 // ------------- forward of token `last_tok` at mel position n, cache row P + n -------------
                 const int pos = p.P + n;
@@ -402,7 +408,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                             }
                         }
                     }
+                    stamp(l * 10 + 0);
                     grid_barrier(p.barrier, epoch, G, tid);
+                    stamp(l * 10 + 1);
                     // ---- ATT: (head, key-range) items ----
                     const int nsplit = min((S + 31) / 32, max(1, G / H));
                     const int chunk = (S + nsplit - 1) / nsplit;
@@ -413,7 +421,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                                              j0, j1, sqrt_hd, att_smem, tid, ConsumerSync(), p.att_o + (size_t)item * HD,
                                              p.att_ml + (size_t)item * 2);
                     }
+                    stamp(l * 10 + 2);
                     grid_barrier(p.barrier, epoch, G, tid);
+                    stamp(l * 10 + 3);
                     // ---- PROJ: merge attention partials -> o ; x += o . W_proj + b ----
                     {
                         float xr[4] = {0.f, 0.f, 0.f, 0.f};
@@ -443,7 +453,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                             p.x[ncolg] = xres + y;
                         }
                     }
+                    stamp(l * 10 + 4);
                     grid_barrier(p.barrier, epoch, G, tid);
+                    stamp(l * 10 + 5);
                     // ---- FC: LN2 -> u = gelu_new(. W_fc + b) ----
                     {
                         float xr[4] = {0.f, 0.f, 0.f, 0.f};
@@ -458,7 +470,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                         const float y = gemv_phase<4, 1>(ring, cs, ncol[PH_FC], D, xr, red, tid);
                         if (tid < ncol[PH_FC]) p.ubuf[cbeg[PH_FC] + tid] = gelu_new(y);
                     }
+                    stamp(l * 10 + 6);
                     grid_barrier(p.barrier, epoch, G, tid);
+                    stamp(l * 10 + 7);
                     // ---- PROJ2: x += u . W_proj2 + b ----
                     {
                         float ur[16];
@@ -475,7 +489,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                             p.x[ncolg] = ldcg(p.x + ncolg) + y;
                         }
                     }
+                    stamp(l * 10 + 8);
                     grid_barrier(p.barrier, epoch, G, tid);
+                    stamp(l * 10 + 9);
                 }
                 // ---- HEAD: ln_f -> final_norm -> latent z ; logits = z . mel_head^T + b ----
                 {
@@ -494,11 +510,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     const float y = gemv_phase<4, 1>(ring, cs, ncol[PH_HEAD], D, xr, red, tid);
                     if (tid < ncol[PH_HEAD]) p.pend_logits[cbeg[PH_HEAD] + tid] = y;
                 }
+                stamp(p.L * 10 + 0);
                 grid_barrier(p.barrier, epoch, G, tid);
+                stamp(p.L * 10 + 1);
             }
             // ------------- sample + emit (every CTA computes the same token) -------------
             int tok = sample_token(p.pend_logits, seen, scfg, p.noise ? p.noise + (size_t)i * p.V : nullptr, p.seed,
                                    (uint32_t)n, 0u, keys, fscr, iscr, tid, ConsumerSync());
+            stamp(p.L * 10 + 2);
             if (p.forced) tok = (int)p.forced[i];
             if (!p.ignore_eos && finished) tok = p.stop_token;
             if (cta == 0) {

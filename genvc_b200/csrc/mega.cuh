@@ -42,6 +42,9 @@ struct MegaParams {
     float* latents_out;   // [n_steps, D]
     float* logits_out;    // [n_steps, V] or null
     int* status;          // {emitted, done}
+    // debug timeline: tid 0 of every CTA stamps %globaltimer at phase boundaries of step `trace_step`
+    unsigned long long* trace;  // [grid][trace_slots] or null
+    int trace_step, trace_slots;
 };
 
 size_t mega_smem_bytes(int D, int nslot, int Vpad);

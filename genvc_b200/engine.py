@@ -257,6 +257,19 @@ class Engine:
                                                    out.data_ptr(), self._stream()))
         return out
 
+    # ------------------------------------------------------------------ debug timeline
+    def trace(self, step: Optional[int] = 0) -> Optional[torch.Tensor]:
+        """Arm (``step`` = index inside each decode launch) or disarm (``None``) the fused kernel's
+        phase timeline; returns the int64 buffer [grid, slots] the kernel writes %globaltimer into."""
+        if step is None:
+            self._check(self.lib.genvc_debug_trace(self._ctx, None, 0, 0))
+            self._trace = None
+            return None
+        slots = self.dims.n_layer * 10 + 8
+        self._trace = torch.zeros((self.decode_grid, slots), dtype=torch.int64, device=self.device)
+        self._check(self.lib.genvc_debug_trace(self._ctx, self._trace.data_ptr(), slots, int(step)))
+        return self._trace
+
     # ------------------------------------------------------------------ microbenchmark
     def kv_attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S: int) -> torch.Tensor:
         """q [N,H,hd]; k, v [N,H,S_max,hd]; attends the first S keys -> [N,H,hd]."""

@@ -166,6 +166,14 @@ int genvc_kv_attention(const float* q_dev, const float* k_dev, const float* v_de
 /* Number of kernels launched by this context since creation (bench bookkeeping). */
 uint64_t genvc_launch_count(const genvc_ctx* ctx);
 
+/* Debug/profiling hook (no reference counterpart): when trace_dev != NULL, thread 0 of
+ * every persistent CTA of the fused decode kernel writes %globaltimer (ns) at each phase
+ * boundary of step `step` of every following genvc_decode launch into
+ * trace_dev[cta * slots_per_cta + slot]; slot = layer*10 + {0..9} (compute end / barrier
+ * end of QKV, ATT, PROJ, FC, PROJ2), n_layer*10 + {0,1,2,3} = head end, barrier end,
+ * sample end, step start.  NULL switches it off. */
+int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, int step);
+
 #ifdef __cplusplus
 }
 #endif
