@@ -22,7 +22,6 @@ using namespace gv;
 namespace {
 
 constexpr size_t kSplitKFloats = size_t(4) << 20;  // deterministic split-K partials (ops.cu)
-constexpr int kMegaSlots = 12;
 
 struct Workspace {
     size_t bytes = 0;
@@ -54,15 +53,19 @@ struct genvc_ctx {
     char* ws = nullptr;
 
     // workspace offsets (bytes)
-    size_t o_barrier, o_state, o_seen, o_status_scratch, o_pend_logits, o_pend_latent, o_mx, o_mq, o_mu, o_matt_o, o_matt_ml,
-        o_splitk, o_X, o_A, o_QKV, o_U;
+    size_t o_state, o_seen, o_status_scratch, o_pend_logits, o_pend_latent, o_splitk, o_X, o_A, o_QKV, o_U;
+    // exchange buffers of the fused decode kernel ({value, tag} pairs; one contiguous region)
+    size_t o_xchg, xchg_bytes, o_xq, o_matt_o, o_matt_ml, o_x1, o_u, o_x2, o_lg;
+    uint32_t tag_next = 1;
     size_t o_pc_melT, o_pc_ctx, o_pc_kv, o_pc_lat, o_pc_q, o_pc_o, o_pc_h, o_pc_g;
     size_t ws_bytes = 0;
     int Vpad = 0;
 
     // debug timeline of the fused decode kernel (genvc_debug_trace)
     unsigned long long* trace = nullptr;
+    unsigned long long* trace2 = nullptr;
     int trace_slots = 0, trace_step = 0;
+    int window = GV_MEGA_NSLOT, dbg_nosync = 0;
 
     // host mirror of the generation state
     int B = 0, P = 0;
@@ -109,18 +112,20 @@ static void plan_workspace(genvc_ctx* c) {
     const size_t D = g.d_model, V = g.n_audio_vocab, MB = g.max_batch, F = sizeof(float);
     c->Vpad = (int)((V + 15) / 16 * 16);
     Workspace w;
-    c->o_barrier = w.take(256);
     c->o_state = w.take(sizeof(GenState) + 64);
     c->o_seen = w.take(MB * c->Vpad);
     c->o_status_scratch = w.take(64);
     c->o_pend_logits = w.take(MB * V * F);
     c->o_pend_latent = w.take(MB * D * F);
-    c->o_mx = w.take(D * F);
-    c->o_mq = w.take(D * F);
-    c->o_mu = w.take(4 * D * F);
     const size_t items = (size_t)std::max(c->grid, 1) + g.n_head;
-    c->o_matt_o = w.take(items * (D / g.n_head) * F);
-    c->o_matt_ml = w.take(items * 2 * F);
+    c->o_xchg = c->o_xq = w.take(2 * 3 * D * F);
+    c->o_matt_o = w.take(2 * items * (D / g.n_head) * F);
+    c->o_matt_ml = w.take(2 * items * 2 * F);
+    c->o_x1 = w.take(2 * D * F);
+    c->o_u = w.take(2 * 4 * D * F);
+    c->o_x2 = w.take(2 * D * F);
+    c->o_lg = w.take(2 * V * F);
+    c->xchg_bytes = w.take(0) - c->o_xchg;
     c->o_splitk = w.take(kSplitKFloats * F);
     const size_t R = c->rows_cap();
     c->o_X = w.take(R * D * F);
@@ -181,7 +186,8 @@ int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
     // column-slice limits of the fused kernel's register tiles (decode_mega.cu: MAXT * CT)
     auto ceil_div = [](int a, int b) { return (a + b - 1) / b; };
     ctx->mega_ok = ceil_div(4 * g.d_model, ctx->grid) <= 32 && ceil_div(g.d_model, ctx->grid) <= 8 &&
-                   ceil_div(g.n_audio_vocab, ctx->grid) <= 32 && g.n_audio_vocab <= 2048;
+                   ceil_div(g.n_audio_vocab, ctx->grid) <= 32 && g.n_audio_vocab <= 2048 &&
+                   (uint64_t)g.max_gen_mel_tokens * (5ull * g.n_layer + 1ull) < 0x7FFFFFFFull;
     plan_workspace(ctx);
     *out = ctx;
     return GENVC_OK;
@@ -267,15 +273,29 @@ int genvc_bind_buffers(genvc_ctx* ctx, float* kv_dev, uint64_t kv_floats, void* 
     ctx->kv = kv_dev;
     ctx->ws = static_cast<char*>(workspace_dev);
     ctx->prefilled = false;
+    // exchange tags start at 1 over zeroed buffers
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemset(ctx->ws + ctx->o_xchg, 0, ctx->xchg_bytes));
+    CK(cudaDeviceSynchronize());
+    ctx->tag_next = 1;
     return GENVC_OK;
 }
 
 uint64_t genvc_launch_count(const genvc_ctx* ctx) { return ctx ? ctx->nlaunch : 0; }
 
+int genvc_debug_tune(genvc_ctx* ctx, int window, int nosync) {
+    if (!ctx) return GENVC_E_INVALID;
+    if (window > 0) ctx->window = std::min(window, (int)GV_MEGA_NSLOT);
+    ctx->dbg_nosync = nosync ? 1 : 0;
+    return GENVC_OK;
+}
+
 int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, int step) {
     if (!ctx) return GENVC_E_INVALID;
     if (trace_dev && (slots_per_cta <= 0 || step < 0)) return ctx->fail(GENVC_E_INVALID, "bad trace geometry");
     ctx->trace = reinterpret_cast<unsigned long long*>(trace_dev);
+    // the tile timeline (layers 10-11 of the traced step) follows the phase timeline in the same buffer
+    ctx->trace2 = trace_dev ? ctx->trace + (size_t)ctx->grid * slots_per_cta : nullptr;
     ctx->trace_slots = trace_dev ? slots_per_cta : 0;
     ctx->trace_step = step;
     return GENVC_OK;
@@ -502,17 +522,27 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         MegaParams p;
         memset(&p, 0, sizeof p);
         p.L = g.n_layer; p.D = D; p.H = g.n_head; p.V = V; p.Vpad = ctx->Vpad; p.S_max = g.max_seq;
-        p.P = ctx->P; p.n_steps = n_steps; p.nslot = kMegaSlots;
+        p.P = ctx->P; p.n_steps = n_steps;
         p.stream = ctx->stream; p.blob = ctx->blob;
         p.ln1_off = (long long)L.layers[0].ln1_w;
         p.ln2_off = (long long)L.layers[0].ln2_w;
         p.layer_stride = g.n_layer > 1 ? (long long)(L.layers[1].ln1_w - L.layers[0].ln1_w) : 0;
         p.lnf_off = (long long)L.lnf_w; p.mel_emb_off = (long long)L.mel_emb; p.mel_pos_off = (long long)L.mel_pos;
         p.kv = ctx->kv; p.kv_layer_stride = (long long)ctx->kv_plane();
-        p.x = ctx->at<float>(ctx->o_mx); p.qbuf = ctx->at<float>(ctx->o_mq); p.ubuf = ctx->at<float>(ctx->o_mu);
-        p.att_o = ctx->at<float>(ctx->o_matt_o); p.att_ml = ctx->at<float>(ctx->o_matt_ml);
+        p.xq = ctx->at<float>(ctx->o_xq); p.att_o = ctx->at<float>(ctx->o_matt_o); p.att_ml = ctx->at<float>(ctx->o_matt_ml);
+        p.x1 = ctx->at<float>(ctx->o_x1); p.u = ctx->at<float>(ctx->o_u); p.x2 = ctx->at<float>(ctx->o_x2);
+        p.lg = ctx->at<float>(ctx->o_lg);
+        {   // exchange tags: unique per (launch, step, layer, buffer); restart over zeroed buffers before a wrap
+            const uint64_t need = (uint64_t)n_steps * (5ull * g.n_layer + 1ull);
+            if ((uint64_t)ctx->tag_next + need >= 0xFFFFFFF0ull) {
+                CK(cudaMemsetAsync(ctx->ws + ctx->o_xchg, 0, ctx->xchg_bytes, st));
+                ctx->tag_next = 1;
+            }
+            p.tag0 = ctx->tag_next;
+            ctx->tag_next += (uint32_t)need;
+        }
         p.pend_logits = ctx->at<float>(ctx->o_pend_logits); p.pend_latent = ctx->at<float>(ctx->o_pend_latent);
-        p.st = gs; p.seen = seen; p.barrier = ctx->at<unsigned>(ctx->o_barrier);
+        p.st = gs; p.seen = seen;
         p.top_k = sp->top_k; p.top_p = sp->top_p; p.top_p_threshold = sp->top_p_threshold; p.temperature = sp->temperature;
         p.rep_penalty = sp->repetition_penalty; p.ignore_eos = sp->ignore_eos; p.stop_token = g.stop_audio;
         p.max_total = max_total; p.seed = sp->seed;
@@ -520,6 +550,8 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         p.ids_out = reinterpret_cast<long long*>(ids_out_dev); p.latents_out = latents_out_dev; p.logits_out = logits_out_dev;
         p.status = status_dev;
         p.trace = ctx->trace; p.trace_slots = ctx->trace_slots; p.trace_step = ctx->trace_step;
+        p.trace2 = ctx->trace2;
+        p.window = ctx->window; p.dbg_nosync = ctx->dbg_nosync;
         CK(launch_decode_mega(p, ctx->grid, st));
         ctx->nlaunch += 1;
         ctx->n_host = std::min(max_total, ctx->n_host + n_steps);

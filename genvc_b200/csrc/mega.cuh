@@ -8,11 +8,12 @@
 
 namespace gv {
 
+#define GV_TRACE2_TILES 32
+
 struct MegaParams {
     int L, D, H, V, Vpad, S_max;
     int P;          // prefix length: cache row of mel position n is P + n
     int n_steps;    // tokens to emit in this launch (at most)
-    int nslot;      // ring depth
     // weights
     const float* stream;  // per-CTA weight streams (stream_layout.h)
     const float* blob;    // reference-layout blob (LayerNorm params, embeddings)
@@ -20,16 +21,19 @@ struct MegaParams {
     // activations / state (global, L2-resident)
     float* kv;
     long long kv_layer_stride;  // floats per (layer, k|v) plane
-    float* x;       // [D] residual stream
-    float* qbuf;    // [D]
-    float* ubuf;    // [4D]
-    float* att_o;   // [items][hd] un-normalised partial outputs
+    // exchange buffers: every element is an 8-byte {value, tag} pair (decode_mega.cu)
+    float* xq;      // [3D] q | k | v of the token being decoded
+    float* att_o;   // [items][hd] un-normalised partial attention outputs
     float* att_ml;  // [items][2]  (max, sum)
+    float* x1;      // [D]  residual stream after attention
+    float* u;       // [4D] gelu(fc)
+    float* x2;      // [D]  residual stream leaving the block
+    float* lg;      // [V]  logits
+    unsigned tag0;  // first exchange tag of this launch (never 0; never reused while data with it is live)
     float* pend_logits;  // [V]
     float* pend_latent;  // [D]
     GenState* st;
     unsigned char* seen;  // [Vpad]
-    unsigned* barrier;
     // sampling
     int top_k;
     float top_p, top_p_threshold, temperature, rep_penalty;
@@ -45,9 +49,13 @@ struct MegaParams {
     // debug timeline: tid 0 of every CTA stamps %globaltimer at phase boundaries of step `trace_step`
     unsigned long long* trace;  // [grid][trace_slots] or null
     int trace_step, trace_slots;
+    unsigned long long* trace2;  // [grid][GV_TRACE2_TILES][3] = {producer issue, consumer wait begin, wait end} or null
+    // tuning / debug knobs (genvc_debug_tune)
+    int window;      // producer: max tiles in flight (1..GV_MEGA_NSLOT)
+    int dbg_nosync;  // consumers do not wait for exchange data (results are garbage; streaming-rate probe)
 };
 
-size_t mega_smem_bytes(int D, int nslot, int Vpad);
+size_t mega_smem_bytes(int D, int Vpad);
 cudaError_t launch_decode_mega(const MegaParams& p, int grid, cudaStream_t st);
 cudaError_t launch_pack_stream(const StreamDims& s, int layer, int ph, const float* W, const float* bias, int w_nk,
                                float* stream, cudaStream_t st);

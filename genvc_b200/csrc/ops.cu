@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(GV_SAMPLE_THREADS) sample_kernel(SampleArgs a,
     unsigned char* seen = a.seen + (size_t)b * a.Vpad;
     SampleCfg c{a.V, a.top_k, a.top_p, a.top_p_threshold, a.temperature, a.rep_penalty};
     const int n = st->n_emitted;
-    int tok = sample_token(lg, seen, c, a.noise ? a.noise + (size_t)b * a.V : nullptr, a.seed, (uint32_t)n, (uint32_t)b,
+    int tok = sample_token([&](int e) { return ldcg(lg + e); }, seen, c, a.noise ? a.noise + (size_t)b * a.V : nullptr, a.seed, (uint32_t)n, (uint32_t)b,
                            keys, fscr, iscr, tid, BlockSync());
     if (a.forced) tok = (int)a.forced[b];
     const int was_finished = st->finished[b];

@@ -32,10 +32,10 @@ __device__ __forceinline__ float key_val(unsigned long long k) { return ord2f((u
 __device__ __forceinline__ int key_idx(unsigned long long k) { return (int)(0xffffffffu - (uint32_t)k); }
 
 // Scratch layout in shared memory (caller provides): keys[GV_SORT_N] (u64), fscr[16] floats, iscr[8] ints.
-// `logits` is read through L2.  `seen[t] != 0` marks ids present in input_ids.  Returns the token
+// `load_logit(e)` returns raw logit e (L2 or shared memory).  `seen[t] != 0` marks ids present in input_ids.  Returns the token
 // (same value in every thread).  `sync` must synchronise exactly the 256 participating threads.
-template <class Sync>
-__device__ int sample_token(const float* __restrict__ logits, const unsigned char* seen, const SampleCfg& c,
+template <class Load, class Sync>
+__device__ int sample_token(Load load_logit, const unsigned char* seen, const SampleCfg& c,
                             const float* __restrict__ noise, unsigned long long seed, uint32_t step, uint32_t row,
                             unsigned long long* keys, float* fscr, int* iscr, int tid, Sync sync) {
     const int V = c.V;
@@ -43,7 +43,7 @@ __device__ int sample_token(const float* __restrict__ logits, const unsigned cha
     for (int e = tid; e < GV_SORT_N; e += GV_SAMPLE_THREADS) {
         unsigned long long key = 0ull;
         if (e < V) {
-            float s = ldcg(logits + e);
+            float s = load_logit(e);
             if (c.rep_penalty != 1.0f && seen[e]) s = (s < 0.0f) ? s * c.rep_penalty : s / c.rep_penalty;
             if (c.temperature != 1.0f) s = s / c.temperature;
             key = ((unsigned long long)f2ord(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)e);

@@ -70,8 +70,10 @@ GV_HD long long ph_offset_in_layer(const StreamDims& s, int ph, int c) {
 }
 GV_HD long long stream_total_floats(const StreamDims& s) { return cta_base(s, s.G); }
 
-// tile geometry of the shared-memory ring
-GV_HD int slot_floats(int D) { return 4 * D + 16; }
-GV_HD int tile_cols(int ph) { return ph == PH_PROJ2 ? 1 : 4; }
+// tile geometry of the shared-memory ring: a tile is 8 columns of a K = D matrix (one per consumer
+// warp) or 2 columns of the K = 4D matrix — 32 KB at D = 1024; GV_MEGA_NSLOT tiles are in flight
+#define GV_MEGA_NSLOT 6
+GV_HD int slot_floats(int D) { return 8 * D + 32; }
+GV_HD int tile_cols(int ph) { return ph == PH_PROJ2 ? 2 : 8; }
 
 }  // namespace gv

@@ -266,9 +266,15 @@ class Engine:
             self._trace = None
             return None
         slots = self.dims.n_layer * 10 + 8
-        self._trace = torch.zeros((self.decode_grid, slots), dtype=torch.int64, device=self.device)
+        g = self.decode_grid
+        self._trace = torch.zeros(g * (slots + 96), dtype=torch.int64, device=self.device)
         self._check(self.lib.genvc_debug_trace(self._ctx, self._trace.data_ptr(), slots, int(step)))
-        return self._trace
+        self.tile_trace = self._trace[g * slots:].view(g, 32, 3)  # {issue, wait begin, wait end} per tile
+        return self._trace[: g * slots].view(g, slots)
+
+    def tune(self, window: int = 0, nosync: bool = False):
+        """Fused-kernel knobs: TMA tiles in flight per SM; ``nosync`` = streaming-rate probe (garbage results)."""
+        self._check(self.lib.genvc_debug_tune(self._ctx, int(window), int(bool(nosync))))
 
     # ------------------------------------------------------------------ microbenchmark
     def kv_attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S: int) -> torch.Tensor:

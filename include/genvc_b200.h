@@ -171,8 +171,17 @@ uint64_t genvc_launch_count(const genvc_ctx* ctx);
  * boundary of step `step` of every following genvc_decode launch into
  * trace_dev[cta * slots_per_cta + slot]; slot = layer*10 + {0..9} (compute end / barrier
  * end of QKV, ATT, PROJ, FC, PROJ2), n_layer*10 + {0,1,2,3} = head end, barrier end,
- * sample end, step start.  NULL switches it off. */
+ * sample end, step start.  The buffer must hold grid * (slots_per_cta + 96) words: behind the
+ * phase timeline, trace_dev[grid*slots_per_cta + (cta*32 + tile)*3 + {0,1,2}] = {producer issue,
+ * consumer wait begin, consumer wait end} of the weight tiles of layers 10-11 of that step.
+ * NULL switches it off. */
 int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, int step);
+
+/* Tuning / debug knobs of the fused decode kernel (no reference counterpart):
+ *   window > 0 : weight tiles the per-SM TMA producer keeps in flight (requested, not landed);
+ *   nosync != 0: consumers do not wait for exchange data — results are garbage; probes the pure
+ *                weight-streaming rate.  Never set outside profiling. */
+int genvc_debug_tune(genvc_ctx* ctx, int window, int nosync);
 
 #ifdef __cplusplus
 }

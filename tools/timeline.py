@@ -59,6 +59,8 @@ def main():
     ap.add_argument("--layers", type=int, default=30)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--mode", type=int, default=0)
+    ap.add_argument("--window", type=int, nargs="*", default=[0])
+    ap.add_argument("--nosync", type=int, default=0)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline.json"))
     args = ap.parse_args()
     from genvc_b200.config import GenVCDims
@@ -77,19 +79,33 @@ def main():
     kw = dict(do_sample=True, top_p=0.85, top_k=1, temperature=0.85, repetition_penalty=2.0, ignore_eos=True,
               max_new_tokens=24, stream_chunk_size=8, decode_mode=args.mode)
     res = {}
-    for rep in range(3):  # warm-up, then two traced runs (steps 2 and 6 of the 2nd launch)
-        tr = eng.trace(step=(2 if rep < 2 else 6))
-        fake = g.compute_embeddings(cond, codes)
-        for _ in g.get_generator(fake_inputs=fake, **kw):
-            pass
-        torch.cuda.synchronize()
-        if rep > 0:
-            res[f"run{rep}"] = analyse(tr, args.layers)
+    for win in args.window:
+        eng.tune(window=win, nosync=bool(args.nosync))
+        for rep in range(3):  # warm-up, then two traced runs (steps 2 and 6 of the 2nd launch)
+            tr = eng.trace(step=(2 if rep < 2 else 6))
+            fake = g.compute_embeddings(cond, codes)
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in g.get_generator(fake_inputs=fake, **kw):
+                pass
+            t1.record()
+            torch.cuda.synchronize()
+            if rep > 0:
+                res[f"win{win}_run{rep}"] = analyse(tr, args.layers)
+                tt = eng.tile_trace.cpu()
+                for c in (0, 5, 77):
+                    row = tt[c]
+                    base = int(row[row > 0].min()) if (row > 0).any() else 0
+                    res[f"win{win}_run{rep}"][f"tiles_cta{c}"] = [[int(v - base) if v > 0 else -1 for v in t] for t in row.tolist()]
+                res[f"win{win}_run{rep}"]["segment_ms"] = t0.elapsed_time(t1)
     eng.trace(None)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
     for k, v in res.items():
-        print(k, "step_us", round(v["step_ns"] / 1e3, 1), "sample_us", round(v["sample_ns"] / 1e3, 2))
+        print(k, "step_us", round(v["step_ns"] / 1e3, 1), "sample_us", round(v["sample_ns"] / 1e3, 2), "segment_ms", round(v["segment_ms"], 3))
+        for c in (0, 5, 77):
+            if f"tiles_cta{c}" in v:
+                print(f"  tiles cta{c} (issue, wait_begin, wait_end ns):", " ".join(f"({a},{b},{d})" for a, b, d in v[f"tiles_cta{c}"] if a >= 0 or b >= 0))
         for name, a in v["phases"].items():
             print(f"  {name:6s} span {a['span']/1e3:7.2f} us  compute med/max {a['compute_med']/1e3:6.2f}/{a['compute_max']/1e3:6.2f}"
                   f"  wait med {a['wait_med']/1e3:6.2f}  skew {a['skew']/1e3:6.2f}")
