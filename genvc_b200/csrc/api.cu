@@ -55,7 +55,7 @@ struct genvc_ctx {
     // workspace offsets (bytes)
     size_t o_state, o_seen, o_status_scratch, o_pend_logits, o_pend_latent, o_splitk, o_X, o_A, o_QKV, o_U;
     // exchange buffers of the fused decode kernel ({value, tag} pairs; one contiguous region)
-    size_t o_xchg, xchg_bytes, o_xq, o_matt_o, o_matt_ml, o_x1, o_u, o_x2, o_lg;
+    size_t o_xchg, xchg_bytes, o_xq, o_matt_o, o_matt_ml, o_x1, o_pp, o_x2, o_lg, o_hops;
     uint32_t tag_next = 1;
     size_t o_pc_melT, o_pc_ctx, o_pc_kv, o_pc_lat, o_pc_q, o_pc_o, o_pc_h, o_pc_g;
     size_t ws_bytes = 0;
@@ -63,9 +63,8 @@ struct genvc_ctx {
 
     // debug timeline of the fused decode kernel (genvc_debug_trace)
     unsigned long long* trace = nullptr;
-    unsigned long long* trace2 = nullptr;
     int trace_slots = 0, trace_step = 0;
-    int window = GV_MEGA_NSLOT, dbg_nosync = 0;
+    int window = 4, dbg_nosync = 0;
 
     // host mirror of the generation state
     int B = 0, P = 0;
@@ -117,14 +116,16 @@ static void plan_workspace(genvc_ctx* c) {
     c->o_status_scratch = w.take(64);
     c->o_pend_logits = w.take(MB * V * F);
     c->o_pend_latent = w.take(MB * D * F);
-    const size_t items = (size_t)std::max(c->grid, 1) + g.n_head;
+    // exchange buffers of the fused decode kernel: {value, tag} pairs (2 floats per element)
+    const size_t items = (size_t)g.n_head * 8;  // att_nsplit() <= 8
     c->o_xchg = c->o_xq = w.take(2 * 3 * D * F);
     c->o_matt_o = w.take(2 * items * (D / g.n_head) * F);
     c->o_matt_ml = w.take(2 * items * 2 * F);
     c->o_x1 = w.take(2 * D * F);
-    c->o_u = w.take(2 * 4 * D * F);
+    c->o_pp = w.take(2 * (size_t)std::max(c->grid, 1) * D * F);
     c->o_x2 = w.take(2 * D * F);
-    c->o_lg = w.take(2 * V * F);
+    c->o_lg = w.take(2 * (size_t)c->Vpad * F);
+    c->o_hops = w.take(HC_COUNT * GV_HOP_STRIDE * sizeof(unsigned));
     c->xchg_bytes = w.take(0) - c->o_xchg;
     c->o_splitk = w.take(kSplitKFloats * F);
     const size_t R = c->rows_cap();
@@ -183,11 +184,14 @@ int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
     // Without a device (CPU-only layout queries) the grid defaults to a B200's 148 SMs.
     ctx->grid = ctx->n_sm > 0 ? ctx->n_sm : 148;
     ctx->sdims = StreamDims{g.n_layer, g.d_model, g.n_audio_vocab, ctx->grid};
-    // column-slice limits of the fused kernel's register tiles (decode_mega.cu: MAXT * CT)
+    // limits of the fused kernel (decode_mega.cu): D = 128 * {1,2,4,8}; at most 32 units of a phase per CTA
+    // (two per consumer warp); attention items (n_head * 8) and the partial-sum gather fit the grid / scratch
     auto ceil_div = [](int a, int b) { return (a + b - 1) / b; };
-    ctx->mega_ok = ceil_div(4 * g.d_model, ctx->grid) <= 32 && ceil_div(g.d_model, ctx->grid) <= 8 &&
-                   ceil_div(g.n_audio_vocab, ctx->grid) <= 32 && g.n_audio_vocab <= 2048 &&
-                   (uint64_t)g.max_gen_mel_tokens * (5ull * g.n_layer + 1ull) < 0x7FFFFFFFull;
+    const int nxv = g.d_model / 128;
+    ctx->mega_ok = (nxv == 1 || nxv == 2 || nxv == 4 || nxv == 8) && ceil_div(4 * g.d_model, ctx->grid) <= 32 &&
+                   ceil_div(g.n_audio_vocab, ctx->grid) <= 32 && g.n_audio_vocab <= 2048 && g.n_head * 8 <= ctx->grid &&
+                   g.d_model / 8 <= ctx->grid && ctx->grid <= 512 &&
+                   (uint64_t)g.max_gen_mel_tokens * ((uint64_t)GV_TAGS_PER_LAYER * g.n_layer + 1ull) < 0x7FFFFFFFull;
     plan_workspace(ctx);
     *out = ctx;
     return GENVC_OK;
@@ -251,7 +255,8 @@ int genvc_pack_stream(genvc_ctx* ctx, float* stream_dev, uint64_t n_floats, void
         CK(launch_pack_stream(ctx->sdims, l, PH_QKV, ctx->w(o.attn_w), ctx->w(o.attn_b), 0, stream_dev, st));
         CK(launch_pack_stream(ctx->sdims, l, PH_PROJ, ctx->w(o.proj_w), ctx->w(o.proj_b), 0, stream_dev, st));
         CK(launch_pack_stream(ctx->sdims, l, PH_FC, ctx->w(o.fc_w), ctx->w(o.fc_b), 0, stream_dev, st));
-        CK(launch_pack_stream(ctx->sdims, l, PH_PROJ2, ctx->w(o.proj2_w), ctx->w(o.proj2_b), 0, stream_dev, st));
+        // mlp.c_proj [4D, D] is split along K: unit k = row k (its bias is added by the reducer CTAs)
+        CK(launch_pack_stream(ctx->sdims, l, PH_P2, ctx->w(o.proj2_w), nullptr, 1, stream_dev, st));
         ctx->nlaunch += 4;
     }
     CK(launch_pack_stream(ctx->sdims, 0, PH_HEAD, ctx->w(L.mel_head_w), ctx->w(L.mel_head_b), 1, stream_dev, st));
@@ -294,8 +299,6 @@ int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, in
     if (!ctx) return GENVC_E_INVALID;
     if (trace_dev && (slots_per_cta <= 0 || step < 0)) return ctx->fail(GENVC_E_INVALID, "bad trace geometry");
     ctx->trace = reinterpret_cast<unsigned long long*>(trace_dev);
-    // the tile timeline (layers 10-11 of the traced step) follows the phase timeline in the same buffer
-    ctx->trace2 = trace_dev ? ctx->trace + (size_t)ctx->grid * slots_per_cta : nullptr;
     ctx->trace_slots = trace_dev ? slots_per_cta : 0;
     ctx->trace_step = step;
     return GENVC_OK;
@@ -526,14 +529,17 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         p.stream = ctx->stream; p.blob = ctx->blob;
         p.ln1_off = (long long)L.layers[0].ln1_w;
         p.ln2_off = (long long)L.layers[0].ln2_w;
+        p.proj2_b_off = (long long)L.layers[0].proj2_b;
         p.layer_stride = g.n_layer > 1 ? (long long)(L.layers[1].ln1_w - L.layers[0].ln1_w) : 0;
         p.lnf_off = (long long)L.lnf_w; p.mel_emb_off = (long long)L.mel_emb; p.mel_pos_off = (long long)L.mel_pos;
         p.kv = ctx->kv; p.kv_layer_stride = (long long)ctx->kv_plane();
         p.xq = ctx->at<float>(ctx->o_xq); p.att_o = ctx->at<float>(ctx->o_matt_o); p.att_ml = ctx->at<float>(ctx->o_matt_ml);
-        p.x1 = ctx->at<float>(ctx->o_x1); p.u = ctx->at<float>(ctx->o_u); p.x2 = ctx->at<float>(ctx->o_x2);
+        p.x1 = ctx->at<float>(ctx->o_x1); p.pp = ctx->at<float>(ctx->o_pp); p.x2 = ctx->at<float>(ctx->o_x2);
         p.lg = ctx->at<float>(ctx->o_lg);
+        p.hops = ctx->at<unsigned>(ctx->o_hops);
+        CK(cudaMemsetAsync(p.hops, 0, HC_COUNT * GV_HOP_STRIDE * sizeof(unsigned), st));
         {   // exchange tags: unique per (launch, step, layer, buffer); restart over zeroed buffers before a wrap
-            const uint64_t need = (uint64_t)n_steps * (5ull * g.n_layer + 1ull);
+            const uint64_t need = (uint64_t)n_steps * ((uint64_t)GV_TAGS_PER_LAYER * g.n_layer + 1ull);
             if ((uint64_t)ctx->tag_next + need >= 0xFFFFFFF0ull) {
                 CK(cudaMemsetAsync(ctx->ws + ctx->o_xchg, 0, ctx->xchg_bytes, st));
                 ctx->tag_next = 1;
@@ -550,7 +556,6 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         p.ids_out = reinterpret_cast<long long*>(ids_out_dev); p.latents_out = latents_out_dev; p.logits_out = logits_out_dev;
         p.status = status_dev;
         p.trace = ctx->trace; p.trace_slots = ctx->trace_slots; p.trace_step = ctx->trace_step;
-        p.trace2 = ctx->trace2;
         p.window = ctx->window; p.dbg_nosync = ctx->dbg_nosync;
         CK(launch_decode_mega(p, ctx->grid, st));
         ctx->nlaunch += 1;

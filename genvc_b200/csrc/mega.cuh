@@ -8,7 +8,13 @@
 
 namespace gv {
 
-#define GV_TRACE2_TILES 32
+// hop counters (one 128-byte line each, zeroed by the host before every launch)
+enum { HC_XQ = 0, HC_AO = 1, HC_X1 = 2, HC_PP = 3, HC_X2 = 4, HC_LG = 5, HC_COUNT = 6 };
+#define GV_HOP_STRIDE 32  // uint32 words between two counters
+// exchange tags of one forward: tag(layer l, buffer b) = tbase + GV_TAGS_PER_LAYER*l + b; logits = tbase + GV_TAGS_PER_LAYER*L
+#define GV_TAGS_PER_LAYER 5
+// debug timeline slots per layer (genvc_debug_trace)
+#define GV_TRACE_PER_LAYER 10
 
 struct MegaParams {
     int L, D, H, V, Vpad, S_max;
@@ -16,8 +22,8 @@ struct MegaParams {
     int n_steps;    // tokens to emit in this launch (at most)
     // weights
     const float* stream;  // per-CTA weight streams (stream_layout.h)
-    const float* blob;    // reference-layout blob (LayerNorm params, embeddings)
-    long long ln1_off, ln2_off, layer_stride, lnf_off, mel_emb_off, mel_pos_off;
+    const float* blob;    // reference-layout blob (LayerNorm params, biases, embeddings)
+    long long ln1_off, ln2_off, proj2_b_off, layer_stride, lnf_off, mel_emb_off, mel_pos_off;
     // activations / state (global, L2-resident)
     float* kv;
     long long kv_layer_stride;  // floats per (layer, k|v) plane
@@ -26,10 +32,11 @@ struct MegaParams {
     float* att_o;   // [items][hd] un-normalised partial attention outputs
     float* att_ml;  // [items][2]  (max, sum)
     float* x1;      // [D]  residual stream after attention
-    float* u;       // [4D] gelu(fc)
+    float* pp;      // [G][D] per-CTA partial sums of mlp.c_proj
     float* x2;      // [D]  residual stream leaving the block
     float* lg;      // [V]  logits
-    unsigned tag0;  // first exchange tag of this launch (never 0; never reused while data with it is live)
+    unsigned* hops;  // [HC_COUNT * GV_HOP_STRIDE] arrival counters, zero at launch
+    unsigned tag0;   // first exchange tag of this launch (never 0; never reused while data with it is live)
     float* pend_logits;  // [V]
     float* pend_latent;  // [D]
     GenState* st;
@@ -49,7 +56,6 @@ struct MegaParams {
     // debug timeline: tid 0 of every CTA stamps %globaltimer at phase boundaries of step `trace_step`
     unsigned long long* trace;  // [grid][trace_slots] or null
     int trace_step, trace_slots;
-    unsigned long long* trace2;  // [grid][GV_TRACE2_TILES][3] = {producer issue, consumer wait begin, wait end} or null
     // tuning / debug knobs (genvc_debug_tune)
     int window;      // producer: max tiles in flight (1..GV_MEGA_NSLOT)
     int dbg_nosync;  // consumers do not wait for exchange data (results are garbage; streaming-rate probe)

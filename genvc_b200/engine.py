@@ -267,10 +267,9 @@ class Engine:
             return None
         slots = self.dims.n_layer * 10 + 8
         g = self.decode_grid
-        self._trace = torch.zeros(g * (slots + 96), dtype=torch.int64, device=self.device)
+        self._trace = torch.zeros(g * slots, dtype=torch.int64, device=self.device)
         self._check(self.lib.genvc_debug_trace(self._ctx, self._trace.data_ptr(), slots, int(step)))
-        self.tile_trace = self._trace[g * slots:].view(g, 32, 3)  # {issue, wait begin, wait end} per tile
-        return self._trace[: g * slots].view(g, slots)
+        return self._trace.view(g, slots)
 
     def tune(self, window: int = 0, nosync: bool = False):
         """Fused-kernel knobs: TMA tiles in flight per SM; ``nosync`` = streaming-rate probe (garbage results)."""

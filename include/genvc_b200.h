@@ -169,12 +169,11 @@ uint64_t genvc_launch_count(const genvc_ctx* ctx);
 /* Debug/profiling hook (no reference counterpart): when trace_dev != NULL, thread 0 of
  * every persistent CTA of the fused decode kernel writes %globaltimer (ns) at each phase
  * boundary of step `step` of every following genvc_decode launch into
- * trace_dev[cta * slots_per_cta + slot]; slot = layer*10 + {0..9} (compute end / barrier
- * end of QKV, ATT, PROJ, FC, PROJ2), n_layer*10 + {0,1,2,3} = head end, barrier end,
- * sample end, step start.  The buffer must hold grid * (slots_per_cta + 96) words: behind the
- * phase timeline, trace_dev[grid*slots_per_cta + (cta*32 + tile)*3 + {0,1,2}] = {producer issue,
- * consumer wait begin, consumer wait end} of the weight tiles of layers 10-11 of that step.
- * NULL switches it off. */
+ * trace_dev[cta * slots_per_cta + slot]; slot = layer*10 + k with k = 0 QKV input ready,
+ * 1 QKV done, 2 attention item done, 3 attention output merged, 4 PROJ done, 5 FC input ready,
+ * 6 FC + mlp.c_proj partial done, 7 partial sums gathered (reducer CTAs), 8 reduce done;
+ * n_layer*10 + {0,1,2,3,4} = head input ready, head done, logits gathered, sample done, step
+ * start.  The buffer must hold grid * slots_per_cta words.  NULL switches it off. */
 int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, int step);
 
 /* Tuning / debug knobs of the fused decode kernel (no reference counterpart):

@@ -17,38 +17,51 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-PHASES = ["QKV", "ATT", "PROJ", "FC", "PROJ2"]
+# trace slots per layer (include/genvc_b200.h): k = 0 QKV input ready, 1 QKV done, 2 ATT item done, 3 attention
+# output merged, 4 PROJ done, 5 FC input ready, 6 FC+P2 done, 7 partials gathered, 8 reduce done
+SEGMENTS = [
+    ("x2 hop + load", None, 0), ("LN1 + QKV gemv", 0, 1), ("attention item", 1, 2), ("AO hop + merge", 2, 3),
+    ("PROJ gemv", 3, 4), ("x1 hop + load", 4, 5), ("LN2 + FC + P2 gemv", 5, 6), ("PP hop", 6, 7), ("gather + reduce", 7, 8),
+]
 
 
 def analyse(tr: torch.Tensor, L: int) -> dict:
+    """Per segment: median over CTAs of the segment duration, averaged over layers; plus the critical path
+    (latest CTA) view: time between the latest stamp of the segment's end and the latest of its start."""
     tr = tr.cpu().double()  # [G, slots] ns
     G = tr.shape[0]
-    start = tr[:, L * 10 + 3]
+    start = tr[:, L * 10 + 4]
     t0 = float(start.min())
-    out = {"grid": G, "phases": {}, "layers": []}
-    acc = {p: {"compute_med": [], "compute_max": [], "wait_med": [], "skew": [], "span": []} for p in PHASES + ["HEAD"]}
-    prev_end = start.clone()
-    for l in range(L + 1):
-        names = PHASES if l < L else ["HEAD"]
-        for k, name in enumerate(names):
-            ce = tr[:, l * 10 + 2 * k]
-            be = tr[:, l * 10 + 2 * k + 1]
-            comp = ce - prev_end
-            wait = be - ce
-            a = acc[name]
-            a["compute_med"].append(float(comp.median()))
-            a["compute_max"].append(float(comp.max()))
-            a["wait_med"].append(float(wait.median()))
-            a["skew"].append(float(ce.max() - ce.min()))
-            a["span"].append(float(be.max() - prev_end.max()))
-            prev_end = be
+    out = {"grid": G, "segments": {}}
+    acc = {name: {"med": [], "max": [], "crit": []} for name, _, _ in SEGMENTS}
+    for l in range(L):
+        for name, a, b in SEGMENTS:
+            if a is None:
+                if l == 0:
+                    continue
+                ta = tr[:, (l - 1) * 10 + 8]
+                ta = torch.where(ta > 0, ta, tr[:, (l - 1) * 10 + 6])  # non-reducer CTAs skip slots 7, 8
+            else:
+                ta = tr[:, l * 10 + a]
+            tb = tr[:, l * 10 + b]
+            ok = (ta > 0) & (tb > 0)
+            if not ok.any():
+                continue
+            d = (tb - ta)[ok]
+            acc[name]["med"].append(float(d.median()))
+            acc[name]["max"].append(float(d.max()))
+            acc[name]["crit"].append(float(tb[ok].max() - ta[ok].max()))
     for name, a in acc.items():
-        out["phases"][name] = {k: round(statistics.mean(v), 1) for k, v in a.items()}
-        out["phases"][name]["n"] = len(a["span"])
-    sample_end = tr[:, L * 10 + 2]
-    out["step_ns"] = float(sample_end.max() - t0)
-    out["sample_ns"] = float((sample_end - prev_end).median())
-    out["sum_span_ns"] = sum(sum(a["span"]) for a in acc.values())
+        out["segments"][name] = {k: round(statistics.mean(v), 1) if v else 0.0 for k, v in a.items()}
+    head = L * 10
+    out["head"] = {
+        "x2 hop + load": float((tr[:, head + 0] - torch.where(tr[:, head - 2] > 0, tr[:, head - 2], tr[:, head - 4])).median()),
+        "2xLN + head gemv": float((tr[:, head + 1] - tr[:, head + 0]).median()),
+        "logits hop + load": float((tr[:, head + 2] - tr[:, head + 1]).median()),
+        "sample": float((tr[:, head + 3] - tr[:, head + 2]).median()),
+    }
+    out["layer_ns"] = float((tr[:, (L - 1) * 10 + 6].max() - tr[:, 0].max()) / max(L - 1, 1)) if L > 1 else 0.0
+    out["step_ns"] = float(tr[:, head + 3].max() - t0)
     return out
 
 
@@ -92,23 +105,16 @@ def main():
             torch.cuda.synchronize()
             if rep > 0:
                 res[f"win{win}_run{rep}"] = analyse(tr, args.layers)
-                tt = eng.tile_trace.cpu()
-                for c in (0, 5, 77):
-                    row = tt[c]
-                    base = int(row[row > 0].min()) if (row > 0).any() else 0
-                    res[f"win{win}_run{rep}"][f"tiles_cta{c}"] = [[int(v - base) if v > 0 else -1 for v in t] for t in row.tolist()]
                 res[f"win{win}_run{rep}"]["segment_ms"] = t0.elapsed_time(t1)
     eng.trace(None)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
     for k, v in res.items():
-        print(k, "step_us", round(v["step_ns"] / 1e3, 1), "sample_us", round(v["sample_ns"] / 1e3, 2), "segment_ms", round(v["segment_ms"], 3))
-        for c in (0, 5, 77):
-            if f"tiles_cta{c}" in v:
-                print(f"  tiles cta{c} (issue, wait_begin, wait_end ns):", " ".join(f"({a},{b},{d})" for a, b, d in v[f"tiles_cta{c}"] if a >= 0 or b >= 0))
-        for name, a in v["phases"].items():
-            print(f"  {name:6s} span {a['span']/1e3:7.2f} us  compute med/max {a['compute_med']/1e3:6.2f}/{a['compute_max']/1e3:6.2f}"
-                  f"  wait med {a['wait_med']/1e3:6.2f}  skew {a['skew']/1e3:6.2f}")
+        print(k, "step_us", round(v["step_ns"] / 1e3, 1), "layer_us", round(v["layer_ns"] / 1e3, 2), "segment_ms",
+              round(v["segment_ms"], 3))
+        for name, a in v["segments"].items():
+            print(f"  {name:20s} med {a['med']/1e3:6.2f} us  max {a['max']/1e3:6.2f}  critical-path {a['crit']/1e3:6.2f}")
+        print("  head:", {n: round(x / 1e3, 2) for n, x in v["head"].items()})
 
 
 if __name__ == "__main__":
