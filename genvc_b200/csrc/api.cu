@@ -252,14 +252,17 @@ int genvc_pack_stream(genvc_ctx* ctx, float* stream_dev, uint64_t n_floats, void
     const Layout& L = ctx->layout;
     for (int l = 0; l < ctx->cfg.n_layer; ++l) {
         const LayerOff& o = L.layers[l];
-        CK(launch_pack_stream(ctx->sdims, l, PH_QKV, ctx->w(o.attn_w), ctx->w(o.attn_b), 0, stream_dev, st));
-        CK(launch_pack_stream(ctx->sdims, l, PH_PROJ, ctx->w(o.proj_w), ctx->w(o.proj_b), 0, stream_dev, st));
-        CK(launch_pack_stream(ctx->sdims, l, PH_FC, ctx->w(o.fc_w), ctx->w(o.fc_b), 0, stream_dev, st));
+        // ln_1 / ln_2 are folded into the matrices that consume them (decode_mega.cu: pack_stream_kernel)
+        CK(launch_pack_stream(ctx->sdims, l, PH_QKV, ctx->w(o.attn_w), ctx->w(o.attn_b), 0, ctx->w(o.ln1_w), ctx->w(o.ln1_b),
+                              stream_dev, st));
+        CK(launch_pack_stream(ctx->sdims, l, PH_PROJ, ctx->w(o.proj_w), ctx->w(o.proj_b), 0, nullptr, nullptr, stream_dev, st));
+        CK(launch_pack_stream(ctx->sdims, l, PH_FC, ctx->w(o.fc_w), ctx->w(o.fc_b), 0, ctx->w(o.ln2_w), ctx->w(o.ln2_b), stream_dev,
+                              st));
         // mlp.c_proj [4D, D] is split along K: unit k = row k (its bias is added by the reducer CTAs)
-        CK(launch_pack_stream(ctx->sdims, l, PH_P2, ctx->w(o.proj2_w), nullptr, 1, stream_dev, st));
+        CK(launch_pack_stream(ctx->sdims, l, PH_P2, ctx->w(o.proj2_w), nullptr, 1, nullptr, nullptr, stream_dev, st));
         ctx->nlaunch += 4;
     }
-    CK(launch_pack_stream(ctx->sdims, 0, PH_HEAD, ctx->w(L.mel_head_w), ctx->w(L.mel_head_b), 1, stream_dev, st));
+    CK(launch_pack_stream(ctx->sdims, 0, PH_HEAD, ctx->w(L.mel_head_w), ctx->w(L.mel_head_b), 1, nullptr, nullptr, stream_dev, st));
     ctx->nlaunch += 1;
     ctx->stream = stream_dev;
     ctx->stream_packed = true;
@@ -527,8 +530,6 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         p.L = g.n_layer; p.D = D; p.H = g.n_head; p.V = V; p.Vpad = ctx->Vpad; p.S_max = g.max_seq;
         p.P = ctx->P; p.n_steps = n_steps;
         p.stream = ctx->stream; p.blob = ctx->blob;
-        p.ln1_off = (long long)L.layers[0].ln1_w;
-        p.ln2_off = (long long)L.layers[0].ln2_w;
         p.proj2_b_off = (long long)L.layers[0].proj2_b;
         p.layer_stride = g.n_layer > 1 ? (long long)(L.layers[1].ln1_w - L.layers[0].ln1_w) : 0;
         p.lnf_off = (long long)L.lnf_w; p.mel_emb_off = (long long)L.mel_emb; p.mel_pos_off = (long long)L.mel_pos;

@@ -40,7 +40,7 @@
 
 namespace gv {
 
-#define MEGA_WARPS 16
+#define MEGA_WARPS 8
 #define MEGA_CONSUMERS (MEGA_WARPS * 32)
 #define MEGA_THREADS (MEGA_CONSUMERS + 32)  // + one producer warp (one working thread)
 #define MEGA_SPIN_LIMIT (1u << 26)
@@ -58,30 +58,64 @@ struct Ring {
 };
 
 // ---------------------------------------------------------------------------------------------
-// stream packing (init time): gather the reference-layout matrices into the per-CTA streams
+// stream packing (init time): gather the reference-layout matrices into the per-CTA streams.
 //   w_nk = 0: unit n = column n of W [K = D, N]  (HF Conv1D);  w_nk = 1: unit n = row n of W [N, D]
+// LayerNorm folding (lnw != null): the block computes  LN(x) . W + b  with
+//   LN(x)_k = (x_k - mean) * rstd * lnw_k + lnb_k,  so
+//   y_n = rstd * ( sum_k x_k (lnw_k W_kn)  -  mean * c1_n ) + c2_n,
+//   c1_n = sum_k lnw_k W_kn,   c2_n = sum_k lnb_k W_kn + b_n.
+// The unit stores W'_kn = lnw_k W_kn followed by {c2_n, c1_n, 0, 0}: the GEMV runs on the RAW
+// activation vector while the statistics are still being reduced; mean / rstd enter in the epilogue.
+// Without folding the pad is {b_n, 0, 0, 0}.
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_stream_kernel(StreamDims s, int layer, int ph, const float* __restrict__ W,
-                                   const float* __restrict__ bias, int w_nk, float* __restrict__ stream) {
+                                   const float* __restrict__ bias, int w_nk, const float* __restrict__ lnw,
+                                   const float* __restrict__ lnb, float* __restrict__ stream) {
     const int N = ph_N(s, ph), D = s.D;
-    const int n = blockIdx.y;
+    const int n = blockIdx.x;
     const int c = col_owner(N, n, s.G);
     long long dst = cta_base(s, c);
     if (ph == PH_HEAD) dst += (long long)s.L * cta_layer_floats(s, c);
     else dst += (long long)layer * cta_layer_floats(s, c) + ph_offset_in_layer(s, ph, c);
     dst += (long long)(n - col_begin(N, c, s.G)) * unit_floats(D);
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < D + 4; k += gridDim.x * blockDim.x) {
-        float v = 0.0f;
-        if (k < D) v = w_nk ? W[(size_t)n * D + k] : W[(size_t)k * N + n];
-        else if (k == D && bias != nullptr) v = bias[n];
+    double c1 = 0.0, c2 = 0.0;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) {
+        const float w = w_nk ? W[(size_t)n * D + k] : W[(size_t)k * N + n];
+        float v = w;
+        if (lnw != nullptr) {
+            v = lnw[k] * w;
+            c1 += (double)v;
+            c2 += (double)lnb[k] * (double)w;
+        }
         stream[dst + k] = v;
+    }
+    __shared__ double r1[32], r2[32];
+    for (int o = 16; o > 0; o >>= 1) {
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        r1[threadIdx.x >> 5] = c1;
+        r2[threadIdx.x >> 5] = c2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            t1 += r1[w];
+            t2 += r2[w];
+        }
+        if (bias != nullptr) t2 += (double)bias[n];
+        stream[dst + D + 0] = (float)t2;
+        stream[dst + D + 1] = (float)t1;
+        stream[dst + D + 2] = 0.0f;
+        stream[dst + D + 3] = 0.0f;
     }
 }
 
 cudaError_t launch_pack_stream(const StreamDims& s, int layer, int ph, const float* W, const float* bias, int w_nk,
-                               float* stream, cudaStream_t st) {
-    dim3 grid((s.D + 4 + 255) / 256, ph_N(s, ph));
-    pack_stream_kernel<<<grid, 256, 0, st>>>(s, layer, ph, W, bias, w_nk, stream);
+                               const float* lnw, const float* lnb, float* stream, cudaStream_t st) {
+    pack_stream_kernel<<<ph_N(s, ph), 256, 0, st>>>(s, layer, ph, W, bias, w_nk, lnw, lnb, stream);
     return cudaGetLastError();
 }
 
@@ -189,139 +223,212 @@ __device__ __forceinline__ void hop_wait(const unsigned* cnt, unsigned target, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// weight ring (consumer side).  Every consumer warp walks every tile in order and arrives on its
-// empty barrier (count = 16 warps) whether or not it read the tile; only readers wait for `full`.
+// weight ring (consumer side).  Tile t of a phase holds units 4t .. 4t+3 and is read by exactly the
+// four warps of group t % 2 (warp = 4 * group + unit % 4); each of them arrives once on the tile's
+// empty barrier (count = 4).  Tiles are addressed by their global index (ring slot = index % NSLOT).
 // ---------------------------------------------------------------------------------------------
 struct Cons {
-    uint32_t slot, phase;  // ring position of the next tile
-    uint32_t tiles;        // tiles consumed so far (same in every consumer thread)
+    uint32_t gt;               // global index of the first tile of the current phase (same in every thread)
+    unsigned long long* wacc;  // debug: accumulates ns spent waiting for weight tiles (null = off)
 };
-__device__ __forceinline__ const float* tile_ptr(const Ring& r, const Cons& cs) {
-    return r.slots + (size_t)cs.slot * r.slot_floats;
-}
-__device__ __forceinline__ void tile_wait(const Ring& r, const Cons& cs) { mbar_wait(&r.full[cs.slot], cs.phase); }
-__device__ __forceinline__ void tile_release(const Ring& r, Cons& cs, int lane) {
+// One elected lane waits on the tile's full barrier; __syncwarp orders the other lanes behind it.
+__device__ __forceinline__ const float* tile_wait(const Ring& r, const Cons& cs, uint32_t idx, int lane) {
+    const uint32_t slot = idx % NSLOT, par = (idx / NSLOT) & 1u;
+    if (lane == 0) {
+        if (cs.wacc != nullptr) {  // debug timeline
+            const unsigned long long t0 = globaltimer_ns();
+            mbar_wait(&r.full[slot], par);
+            *cs.wacc += globaltimer_ns() - t0;
+        } else {
+            mbar_wait(&r.full[slot], par);
+        }
+    }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&r.empty[cs.slot]);
-    cs.tiles += 1;
-    if (++cs.slot == NSLOT) {
-        cs.slot = 0;
-        cs.phase ^= 1u;
+    return r.slots + (size_t)slot * r.slot_floats;
+}
+__device__ __forceinline__ void tile_release(const Ring& r, uint32_t idx, int lane, uint32_t count = 1u) {
+    __syncwarp();
+    if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&r.empty[idx % NSLOT])), "r"(count) : "memory");
+}
+
+// sum of the per-warp partials red[0..7] (written before a block barrier)
+__device__ __forceinline__ float sum8(const float* red) {
+    const float4 a = *reinterpret_cast<const float4*>(red), b = *reinterpret_cast<const float4*>(red + 4);
+    return ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm statistics of the vector held four elements per thread (thread t owns x[4t .. 4t+3]).
+// One pass over data shifted by `shift` (any value near the mean keeps E[d^2] - E[d]^2 free of
+// cancellation; the callers pass the mean this LayerNorm saw one layer earlier):
+//   stats_partial : per-warp sums of d and d^2 -> red[0..7], red[8..15]   (then ONE block barrier)
+//   stats_finish  : mean, rstd from the 16 partials (every thread, after the barrier)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stats_partial(const float4& x, bool valid, float shift, float* red, int lane, int warp) {
+    float s1 = 0.0f, s2 = 0.0f;
+    if (valid) {
+        const float d0 = x.x - shift, d1 = x.y - shift, d2 = x.z - shift, d3 = x.w - shift;
+        s1 = (d0 + d1) + (d2 + d3);
+        s2 = fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+        red[warp] = s1;
+        red[8 + warp] = s2;
     }
 }
-
-// sum of the per-warp partials red[0..15] (written before a block barrier)
-__device__ __forceinline__ float sum16(const float* red) {
-    const float4 a = *reinterpret_cast<const float4*>(red), b = *reinterpret_cast<const float4*>(red + 4);
-    const float4 c = *reinterpret_cast<const float4*>(red + 8), d = *reinterpret_cast<const float4*>(red + 12);
-    return (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) +
-           (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+__device__ __forceinline__ void stats_finish(const float* red, float inv_d, float shift, float& mean, float& rstd) {
+    const float m = sum8(red) * inv_d;
+    float var = fmaf(-m, m, sum8(red + 8) * inv_d);
+    var = fmaxf(var, 0.0f);
+    mean = shift + m;
+    rstd = rsqrtf(var + 1e-5f);
+    rstd = rstd * fmaf(-0.5f * (var + 1e-5f) * rstd, rstd, 1.5f);  // one Newton step: full fp32 accuracy
 }
-
-// ---------------------------------------------------------------------------------------------
-// LayerNorm of the vector held two elements per thread (thread t owns x[2t], x[2t+1]; valid: 2t < D).
-// Two-pass statistics (mean, then centred sum of squares), two block barriers.  `red` is a 32-float
-// scratch; w / b in shared memory.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ln_pair(float& x0, float& x1, bool valid, int D, const float* w, const float* b, float* red,
-                                        int tid) {
+// explicit LayerNorm (logits head only: its output is the latent handed to the vocoder); two block barriers
+__device__ __forceinline__ void ln_quad(float4& x, bool valid, int D, const float* w, const float* b, float* red, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
-    float s = valid ? (x0 + x1) : 0.0f;
+    float s = valid ? ((x.x + x.y) + (x.z + x.w)) : 0.0f;
     s = warp_sum(s);
     if (lane == 0) red[warp] = s;
     bar_sync(1, MEGA_CONSUMERS);
-    const float mean = sum16(red) / (float)D;
-    const float d0 = x0 - mean, d1 = x1 - mean;
-    float q = valid ? fmaf(d0, d0, d1 * d1) : 0.0f;
+    const float mean = sum8(red) / (float)D;
+    const float d0 = x.x - mean, d1 = x.y - mean, d2 = x.z - mean, d3 = x.w - mean;
+    float q = valid ? (fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3)) : 0.0f;
     q = warp_sum(q);
-    if (lane == 0) red[16 + warp] = q;
+    if (lane == 0) red[8 + warp] = q;
     bar_sync(1, MEGA_CONSUMERS);
-    const float var = sum16(red + 16) / (float)D;
+    const float var = sum8(red + 8) / (float)D;
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
     if (valid) {
-        const float2 ww = *reinterpret_cast<const float2*>(w + 2 * tid);
-        const float2 bb = *reinterpret_cast<const float2*>(b + 2 * tid);
-        x0 = d0 * rstd * ww.x + bb.x;
-        x1 = d1 * rstd * ww.y + bb.y;
+        const float4 ww = *reinterpret_cast<const float4*>(w + 4 * tid);
+        const float4 bb = *reinterpret_cast<const float4*>(b + 4 * tid);
+        x.x = d0 * rstd * ww.x + bb.x;
+        x.y = d1 * rstd * ww.y + bb.y;
+        x.z = d2 * rstd * ww.z + bb.z;
+        x.w = d3 * rstd * ww.w + bb.w;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// GEMV, K = D, one warp per unit: unit u of the phase is handled by warp u % 16 (u < nunits <= 32).
-// `xs` is the activation vector in shared memory (complete: the caller synchronised).  For every
-// unit, lane 0 (u < 16) or lane 16 (u >= 16) of the owning warp calls epi(u, y) with
-//   y = bias + sum_k x_k W[k][unit].
+// GEMV, K = D, one warp per unit: unit u of the phase is handled by warp u % 8 (u < nunits <= 32,
+// up to four units per warp).  `xs` is the activation vector in shared memory (complete: the
+// caller synchronised).  For every unit, lane 8q (q = u / 8) of the owning warp calls
+// epi(u, dot, c2, c1) with  dot = sum_k x_k W'[k][unit]  and the unit's two epilogue constants
+// (pack_stream_kernel).
 // ---------------------------------------------------------------------------------------------
 template <int NXV, class Epi>
-__device__ __forceinline__ void gemv_dot(const Ring& ring, Cons& cs, int nunits, const float* xs, int warp, int lane, Epi epi) {
+__device__ __forceinline__ void gemv_dot(const Ring& ring, const Cons& cs, int nunits, const float* xs, int warp, int lane,
+                                         Epi epi) {
     constexpr int D = NXV * 128, UF = D + 4;
     float4 xv[NXV];
 #pragma unroll
     for (int i = 0; i < NXV; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + (i * 32 + lane) * 4);
-    float tot0 = 0.0f, tot1 = 0.0f;
-    const int ntiles = (nunits + UPT - 1) / UPT;
-    for (int t = 0; t < ntiles; ++t) {
-        if ((t & 3) == (warp >> 2) && t * UPT + (warp & 3) < nunits) {
-            tile_wait(ring, cs);
-            const float* col = tile_ptr(ring, cs) + (warp & 3) * UF;
-            float a0 = (lane == 0) ? col[D] : 0.0f;  // bias folded into the first partial
-            float a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    float tot[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float2 cc[4];
 #pragma unroll
-            for (int i = 0; i < NXV; ++i) {
-                const float4 wv = *reinterpret_cast<const float4*>(col + (i * 32 + lane) * 4);
-                a0 = fmaf(wv.x, xv[i].x, a0);
-                a1 = fmaf(wv.y, xv[i].y, a1);
-                a2 = fmaf(wv.z, xv[i].z, a2);
-                a3 = fmaf(wv.w, xv[i].w, a3);
+    for (int k = 0; k < 4; ++k) cc[k] = make_float2(0.f, 0.f);
+    const int ntiles = (nunits + UPT - 1) / UPT;
+    const int g = warp >> 2, r = warp & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int t = g + 2 * k;
+        if (t < ntiles) {
+            const uint32_t idx = cs.gt + (uint32_t)t;
+            if (t * UPT + r < nunits) {
+                const float* col = tile_wait(ring, cs, idx, lane) + r * UF;
+                cc[k] = *reinterpret_cast<const float2*>(col + D);
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < NXV; ++i) {
+                    const float4 wv = *reinterpret_cast<const float4*>(col + (i * 32 + lane) * 4);
+                    a0 = fmaf(wv.x, xv[i].x, a0);
+                    a1 = fmaf(wv.y, xv[i].y, a1);
+                    a2 = fmaf(wv.z, xv[i].z, a2);
+                    a3 = fmaf(wv.w, xv[i].w, a3);
+                }
+                tot[k] = (a0 + a1) + (a2 + a3);
             }
-            const float sum = (a0 + a1) + (a2 + a3);
-            if (t < 4) tot0 = sum;
-            else tot1 = sum;
+            tile_release(ring, idx, lane);
         }
-        tile_release(ring, cs, lane);
     }
-    // lanes 0..15 reduce tot0, lanes 16..31 reduce tot1
-    const bool up = (lane & 16) != 0;
-    const float keep = up ? tot1 : tot0, send = up ? tot0 : tot1;
-    float v = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    // transposing butterfly: lanes [8q, 8q+8) end up reducing tot[q]
+    const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+    const float k0 = up16 ? tot[2] : tot[0], s0 = up16 ? tot[0] : tot[2];
+    const float k1 = up16 ? tot[3] : tot[1], s1 = up16 ? tot[1] : tot[3];
+    const float h0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);  // tot[0] (lanes < 16) / tot[2]
+    const float h1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);  // tot[1] (lanes < 16) / tot[3]
+    const float keep = up8 ? h1 : h0, send = up8 ? h0 : h1;
+    float v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
     v += __shfl_xor_sync(0xffffffffu, v, 4);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     v += __shfl_xor_sync(0xffffffffu, v, 1);
-    const int u = warp + (up ? 16 : 0);
-    if ((lane & 15) == 0 && u < nunits) epi(u, v);
+    const int q = lane >> 3;
+    const int u = warp + 8 * q;
+    const float2 c = up16 ? (up8 ? cc[3] : cc[2]) : (up8 ? cc[1] : cc[0]);
+    if ((lane & 7) == 0 && u < nunits) epi(u, v, c.x, c.y);
 }
 
-// mlp.c_proj split along K: unit k = row of W_proj2 owned by this CTA; acc{0,1} += u_k * W[k][2t, 2t+1]
+// mlp.c_proj split along K: unit k = row of W_proj2 owned by this CTA.  Warp group g takes tiles
+// t = g, g + 2, ...; thread j of the group (0..127) owns outputs [4j, 4j+4) and [D/2 + 4j, D/2 + 4j + 4) and
+// accumulates u_k * W[k][.] over the group's rows; the two group partials land in part[g][D].
 template <int NXV>
-__device__ __forceinline__ void gemv_outer(const Ring& ring, Cons& cs, int nunits, const float* us, int tid, int lane,
-                                           float& acc0, float& acc1) {
-    constexpr int D = NXV * 128, UF = D + 4;
-    const bool valid = 2 * tid < D;
+__device__ __forceinline__ void gemv_outer(const Ring& ring, const Cons& cs, int nunits, const float* us, int tid, int lane,
+                                           int warp, float* part) {
+    constexpr int D = NXV * 128, UF = D + 4, HALF = D / 2;
+    const int g = warp >> 2, j = tid & 127;
+    const bool valid = 4 * j < HALF;
     const int ntiles = (nunits + UPT - 1) / UPT;
-    for (int t = 0; t < ntiles; ++t) {
-        tile_wait(ring, cs);
-        const float* base = tile_ptr(ring, cs) + 2 * tid;
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int r = 0; r < UPT; ++r) {
-            const int k = t * UPT + r;
-            if (k < nunits && valid) {
-                const float uk = us[k];
-                const float2 w = *reinterpret_cast<const float2*>(base + r * UF);
-                acc0 = fmaf(uk, w.x, acc0);
-                acc1 = fmaf(uk, w.y, acc1);
+    for (int k = 0; k < 4; ++k) {
+        const int t = g + 2 * k;
+        if (t < ntiles) {
+            const uint32_t idx = cs.gt + (uint32_t)t;
+            const float* base = tile_wait(ring, cs, idx, lane) + 4 * j;
+#pragma unroll
+            for (int r = 0; r < UPT; ++r) {
+                const int kk = t * UPT + r;
+                if (kk < nunits && valid) {
+                    const float uk = us[kk];
+                    const float4 w0 = *reinterpret_cast<const float4*>(base + r * UF);
+                    const float4 w1 = *reinterpret_cast<const float4*>(base + r * UF + HALF);
+                    acc0.x = fmaf(uk, w0.x, acc0.x); acc0.y = fmaf(uk, w0.y, acc0.y);
+                    acc0.z = fmaf(uk, w0.z, acc0.z); acc0.w = fmaf(uk, w0.w, acc0.w);
+                    acc1.x = fmaf(uk, w1.x, acc1.x); acc1.y = fmaf(uk, w1.y, acc1.y);
+                    acc1.z = fmaf(uk, w1.z, acc1.z); acc1.w = fmaf(uk, w1.w, acc1.w);
+                }
             }
+            tile_release(ring, idx, lane);
         }
-        tile_release(ring, cs, lane);
+    }
+    if (valid) {
+        *reinterpret_cast<float4*>(part + g * D + 4 * j) = acc0;
+        *reinterpret_cast<float4*>(part + g * D + HALF + 4 * j) = acc1;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// single-query attention over one (head, key range) item, 16 warps.  Arithmetic of HF
-// GPT2Attention._attn for q_len == 1:  s_j = (q . k_j) / sqrt(hd);  p = softmax_j(s);  o = sum_j p_j v_j
-// as an online softmax: key j0 + w + 16 g belongs to warp w; the 16 warp states are merged through
-// shared memory.  The first group's K/V rows are requested before the hop wait for q.
+// single-query attention over one (head, key range) item, 8 warps, built for a short dependency
+// chain.  Arithmetic of HF GPT2Attention._attn for q_len == 1:
+//   s_j = (q . k_j) / sqrt(hd);  p = softmax_j(s);  o = sum_j p_j v_j       (un-normalised here)
+//   * before the hop wait for q: K rows of the first 32 keys (warp w: rows w, w + 8, w + 16, w + 24)
+//     and the V elements of the first 32 keys (thread (ks, d) = (tid / HD, tid % HD): keys ks,
+//     ks + NS, ...) are requested from the cache;
+//   * after it: q (every warp), and for the position being decoded k/v of this very step from the
+//     exchange buffer (appended to the cache by the threads that hold them);
+//   * scores: one warp per key, dot + shuffle tree -> shared memory; barrier;
+//   * every warp computes the softmax weights of all (<= 160) keys redundantly (lane l: keys l,
+//     l + 32, ...), so p_j reaches the PV threads by a shuffle, not a barrier;
+//   * PV: thread (ks, d) accumulates its keys; the NS = 256 / HD partials meet in shared memory.
 // ---------------------------------------------------------------------------------------------
+#define ATT_MAX_BLOCKS 5  // 32-key blocks per item (att_chunk(S) <= 160)
+#define ATT_ROWS 4        // K rows per warp per block (32 keys / 8 warps)
 template <int HD>
 struct AttLane {
     static constexpr int VEC = (HD >= 128) ? 4 : (HD / 32);  // floats per lane per chunk
@@ -349,113 +456,128 @@ __device__ __forceinline__ void st_vec(float* p, const float* r) {
 
 template <int HD>
 __device__ void att_item(float* __restrict__ Kc, float* __restrict__ Vc, const float* xq, int D, int h, int j0, int j1, int S,
-                         uint32_t tag_in, const unsigned* cnt_in, unsigned target_in, float* so, float* sml, int tid,
+                         uint32_t tag_in, const unsigned* cnt_in, unsigned target_in, float* sc, float* opart, int tid,
                          float* o_out, float* ml_out, int item, uint32_t tag_out, uint32_t tmask) {
     using L = AttLane<HD>;
-    constexpr int VEC = L::VEC, NCH = L::NCH, DPL = L::DPL, UNR = 2;
+    constexpr int VEC = L::VEC, NCH = L::NCH, DPL = L::DPL;
+    constexpr int NS = MEGA_CONSUMERS / HD;  // key slices of the PV stage
+    constexpr int VPRE = 32 / NS;            // V elements per thread per 32-key block
     const int warp = tid >> 5, lane = tid & 31;
+    const int ks = tid / HD, d = tid % HD;
+    const int nk = j1 - j0;
+    const int jn = S - 1 - j0;  // relative index of the position being decoded (inside this item iff 0 <= jn < nk)
     const float sqrt_hd = sqrtf((float)HD);
-    float m = -INFINITY, l = 0.0f;
-    float o[DPL], qr[DPL];
+
+    auto load_k_row = [&](int jr, float* dst) {  // cache row of relative key jr (zeros outside the range / for the new key)
+        if (jr < nk && jr != jn) {
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) {
-        o[i] = 0.0f;
-        qr[i] = 0.0f;
-    }
-    float kr[UNR][DPL], vr[UNR][DPL];
-    auto load_group = [&](int jb) {
+            for (int c = 0; c < NCH; ++c) ld_vec<VEC>(Kc + (size_t)(j0 + jr) * HD + (c * 32 + lane) * VEC, dst + c * VEC);
+        } else {
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int j = jb + u * MEGA_WARPS;
-            if (j < j1 && j != S - 1) {
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    ld_vec<VEC>(Kc + (size_t)j * HD + (c * 32 + lane) * VEC, kr[u] + c * VEC);
-                    ld_vec<VEC>(Vc + (size_t)j * HD + (c * 32 + lane) * VEC, vr[u] + c * VEC);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < DPL; ++i) {
-                    kr[u][i] = 0.0f;
-                    vr[u][i] = 0.0f;
-                }
-            }
+            for (int i = 0; i < DPL; ++i) dst[i] = 0.0f;
         }
     };
-    load_group(j0 + warp);       // cache rows: independent of this step's q
+    auto load_v = [&](int jr) -> float { return (jr < nk && jr != jn) ? ldcg(Vc + (size_t)(j0 + jr) * HD + d) : 0.0f; };
+
+    // ---- prefetch block 0 from the cache (independent of this step's q) ----
+    float kr[ATT_ROWS][DPL], vr[VPRE];
+#pragma unroll
+    for (int u = 0; u < ATT_ROWS; ++u) load_k_row(warp + MEGA_WARPS * u, kr[u]);
+#pragma unroll
+    for (int i = 0; i < VPRE; ++i) vr[i] = load_v(ks + NS * i);
     hop_wait(cnt_in, target_in, tid, tmask);
+    // ---- this step's q, and k / v of the position being decoded ----
+    float qr[DPL];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) ld_tagged_vec<VEC>(xq, h * HD + (c * 32 + lane) * VEC, tag_in, tmask, qr + c * VEC);
-    for (int jb = j0 + warp; jb < j1; jb += UNR * MEGA_WARPS) {
-        if (jb != j0 + warp) load_group(jb);
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int j = jb + u * MEGA_WARPS;
-            if (j == S - 1 && j < j1) {  // the position being decoded: k/v of this very step, appended to the cache
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    const int e = h * HD + (c * 32 + lane) * VEC;
-                    ld_tagged_vec<VEC>(xq, D + e, tag_in, tmask, kr[u] + c * VEC);
-                    ld_tagged_vec<VEC>(xq, 2 * D + e, tag_in, tmask, vr[u] + c * VEC);
-                    st_vec<VEC>(Kc + (size_t)j * HD + (c * 32 + lane) * VEC, kr[u] + c * VEC);
-                    st_vec<VEC>(Vc + (size_t)j * HD + (c * 32 + lane) * VEC, vr[u] + c * VEC);
-                }
-            }
-        }
-        float s[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            float d = 0.0f;
-#pragma unroll
-            for (int i = 0; i < DPL; ++i) d = fmaf(qr[i], kr[u][i], d);
-            s[u] = d;
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], off);
-        }
-        float mnew = m;
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            s[u] = (jb + u * MEGA_WARPS < j1) ? s[u] / sqrt_hd : -INFINITY;
-            mnew = fmaxf(mnew, s[u]);
-        }
-        const float corr = expf(m - mnew);  // m == -inf on the first group -> 0
-        l *= corr;
-#pragma unroll
-        for (int i = 0; i < DPL; ++i) o[i] *= corr;
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const float pr = expf(s[u] - mnew);  // masked -> exp(-inf) = 0
-            l += pr;
-#pragma unroll
-            for (int i = 0; i < DPL; ++i) o[i] = fmaf(pr, vr[u][i], o[i]);
-        }
-        m = mnew;
+    float vnew = 0.0f;
+    const bool v_mine = jn >= 0 && jn < nk && (jn % NS) == ks;  // this thread's key slice contains the new position
+    if (v_mine) {
+        vnew = ld_tagged1(xq, 2 * D + h * HD + d, tag_in, tmask);
+        __stcg(Vc + (size_t)(S - 1) * HD + d, vnew);
     }
-    // merge the 16 warp states: so [warp][HD], sml [warp][2]
+    auto new_k_row = [&](float* dst) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
+        for (int c = 0; c < NCH; ++c) {
+            ld_tagged_vec<VEC>(xq, D + h * HD + (c * 32 + lane) * VEC, tag_in, tmask, dst + c * VEC);
+            st_vec<VEC>(Kc + (size_t)(S - 1) * HD + (c * 32 + lane) * VEC, dst + c * VEC);
+        }
+    };
+    // ---- scores ----
+    for (int b = 0; b * 32 < nk; ++b) {
+        if (b > 0) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) so[warp * HD + (c * 32 + lane) * VEC + v] = o[c * VEC + v];
-    if (lane == 0) {
-        sml[warp * 2] = m;
-        sml[warp * 2 + 1] = l;
+            for (int u = 0; u < ATT_ROWS; ++u) load_k_row(b * 32 + warp + MEGA_WARPS * u, kr[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < ATT_ROWS; ++u) {
+            const int jr = b * 32 + warp + MEGA_WARPS * u;
+            if (jr == jn && jr < nk) new_k_row(kr[u]);
+        }
+        float s[ATT_ROWS];
+#pragma unroll
+        for (int u = 0; u < ATT_ROWS; ++u) {
+            float a = 0.0f;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) a = fmaf(qr[i], kr[u][i], a);
+            s[u] = a;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < ATT_ROWS; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < ATT_ROWS; ++u) sc[b * 32 + warp + MEGA_WARPS * u] = s[u] / sqrt_hd;
+        }
     }
     bar_sync(1, MEGA_CONSUMERS);
-    if (tid < HD) {
-        float M = -INFINITY;
+    // ---- softmax weights (every warp, all keys) ----
+    float pv[ATT_MAX_BLOCKS];
+    float M = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < MEGA_WARPS; ++w) M = fmaxf(M, sml[w * 2]);
-        float Lsum = 0.0f, acc = 0.0f;
+    for (int b = 0; b < ATT_MAX_BLOCKS; ++b) {
+        pv[b] = (b * 32 + lane < nk) ? sc[b * 32 + lane] : -INFINITY;
+        M = fmaxf(M, pv[b]);
+    }
+    M = warp_max(M);
+    float Lsum = 0.0f;
 #pragma unroll
-        for (int w = 0; w < MEGA_WARPS; ++w) {
-            const float wgt = (sml[w * 2] == -INFINITY) ? 0.0f : expf(sml[w * 2] - M);
-            Lsum += sml[w * 2 + 1] * wgt;
-            acc = fmaf(so[w * HD + tid], wgt, acc);
+    for (int b = 0; b < ATT_MAX_BLOCKS; ++b) {
+        pv[b] = expf(pv[b] - M);  // outside the range: exp(-inf) = 0
+        Lsum += pv[b];
+    }
+    Lsum = warp_sum(Lsum);
+    // ---- PV ----
+    float o = 0.0f;
+#pragma unroll
+    for (int b = 0; b < ATT_MAX_BLOCKS; ++b) {
+        if (b * 32 < nk) {  // warp-uniform
+            if (b > 0) {
+#pragma unroll
+                for (int i = 0; i < VPRE; ++i) vr[i] = load_v(b * 32 + ks + NS * i);
+            }
+#pragma unroll
+            for (int i = 0; i < VPRE; ++i) {
+                const int jr = b * 32 + ks + NS * i;
+                const float pj = __shfl_sync(0xffffffffu, pv[b], ks + NS * i);
+                const float vj = (jr == jn) ? vnew : vr[i];
+                o = fmaf(pj, vj, o);
+            }
         }
-        st_tagged(o_out, item * HD + tid, acc, tag_out);
+    }
+    if constexpr (NS > 1) {
+        opart[ks * HD + d] = o;
+        bar_sync(1, MEGA_CONSUMERS);
+        if (tid < HD) {
+            o = 0.0f;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) o += opart[q * HD + tid];
+        }
+    }
+    if (tid < HD) {
+        st_tagged(o_out, item * HD + tid, o, tag_out);
         if (tid == 0) st_tagged2(ml_out, item * 2, M, Lsum, tag_out);
     }
 }
@@ -516,14 +638,10 @@ __device__ bool produce_forward(Producer& pr, const MegaParams& p, const StreamD
     for (int ph = 0; ph < 5; ++ph) nun[ph] = ph_units(sd, ph, cta);
     for (int l = 0; l < p.L; ++l) {
         const float* lw = base + (long long)l * lfl;
-        if (!pr.issue(p.blob + p.ln1_off + (long long)l * p.layer_stride, 2 * D, false)) return false;
-        if (!pr.issue_units(lw, nun[PH_QKV], uf)) return false;
-        if (!pr.issue_units(lw, nun[PH_PROJ], uf)) return false;
-        if (!pr.issue(p.blob + p.ln2_off + (long long)l * p.layer_stride, 2 * D, false)) return false;
-        if (!pr.issue_units(lw, nun[PH_FC], uf)) return false;
-        if (!pr.issue_units(lw, nun[PH_P2], uf)) return false;
+        for (int ph = PH_QKV; ph <= PH_P2; ++ph)
+            if (!pr.issue_units(lw, nun[ph], uf)) return false;
     }
-    if (!pr.issue(p.blob + p.lnf_off, 4 * D, false)) return false;
+    if (!pr.issue(p.blob + p.lnf_off, 4 * D, false)) return false;  // ln_f and final_norm parameters
     const float* hw = base + (long long)p.L * lfl;
     return pr.issue_units(hw, nun[PH_HEAD], uf);
 }
@@ -547,19 +665,21 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     ring.slots = reinterpret_cast<float*>(smem_raw);
     off += (size_t)NSLOT * ring.slot_floats * sizeof(float);
     off = (off + 127) & ~size_t(127);
-    // scratch region: sampling sort keys | attention merge buffer | partial-sum gather (never live together)
+    // scratch region: sampling sort keys | attention scores + PV partials | mlp.c_proj group partials |
+    // partial-sum gather (never live together)
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + off);
-    float* att_so = reinterpret_cast<float*>(smem_raw + off);            // [16][HD]  (<= 16 KB)
-    float* att_sml = reinterpret_cast<float*>(smem_raw + off + 16384);   // [16][2]
+    float* att_sc = reinterpret_cast<float*>(smem_raw + off);            // [160]
+    float* att_op = reinterpret_cast<float*>(smem_raw + off + 1024);     // [256]
+    float* part = reinterpret_cast<float*>(smem_raw + off);              // [2][D]
     float* gat = reinterpret_cast<float*>(smem_raw + off);               // [G][8]
     off += MEGA_SCRATCH_BYTES;
     float* slog = reinterpret_cast<float*>(smem_raw + off);  // [Vpad] logits of the step being sampled
     off += (size_t)p.Vpad * sizeof(float);
-    float* xres0 = reinterpret_cast<float*>(smem_raw + off);  // [D] residual stream entering the block
+    float* xres0 = reinterpret_cast<float*>(smem_raw + off);  // [D] residual stream entering the block (= QKV GEMV input)
     off += (size_t)D * sizeof(float);
-    float* xres1 = reinterpret_cast<float*>(smem_raw + off);  // [D] residual stream after attention
+    float* xres1 = reinterpret_cast<float*>(smem_raw + off);  // [D] residual stream after attention (= FC GEMV input)
     off += (size_t)D * sizeof(float);
-    float* xn = reinterpret_cast<float*>(smem_raw + off);  // [D] GEMV input vector
+    float* xo = reinterpret_cast<float*>(smem_raw + off);  // [D] attention output (PROJ input) / latent (head input)
     off += (size_t)D * sizeof(float);
     ring.full = reinterpret_cast<uint64_t*>(smem_raw + off);
     off += 16 * sizeof(uint64_t);
@@ -567,8 +687,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     off += 16 * sizeof(uint64_t);
     float* us = reinterpret_cast<float*>(smem_raw + off);  // [32] this CTA's gelu(fc) values
     off += 32 * sizeof(float);
-    float* red = reinterpret_cast<float*>(smem_raw + off);  // [32] LayerNorm statistics
-    off += 32 * sizeof(float);
+    float* red = reinterpret_cast<float*>(smem_raw + off);  // [2][16] LayerNorm statistics (ln_1 | ln_2)
+    off += 64 * sizeof(float);
     float* fscr = reinterpret_cast<float*>(smem_raw + off);
     off += 16 * sizeof(float);
     int* iscr = reinterpret_cast<int*>(smem_raw + off);
@@ -580,7 +700,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     if (tid_all == 0) {
         for (int i = 0; i < NSLOT; ++i) {
             mbar_init(&ring.full[i], 1);
-            mbar_init(&ring.empty[i], MEGA_WARPS);
+            mbar_init(&ring.empty[i], 4);  // the four reader warps of a tile
         }
         ctl[0] = 0;
         ctl[1] = 0;
@@ -624,16 +744,19 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     // ================= consumer warps =================
     const int tid = tid_all;
     const int lane = tid & 31, warp = tid >> 5;
-    Cons cs{0u, 0u, 0u};
+    Cons cs{0u, nullptr};
+    unsigned long long wait_ns = 0;
     const uint32_t tmask = p.dbg_nosync ? 0u : 0xffffffffu;  // debug: 0 = do not wait for exchange data
-    const bool xvalid = 2 * tid < D;
+    const bool xvalid = 4 * tid < D;                         // thread t owns elements 4t .. 4t+3 of every D-vector
+    const float inv_d = 1.0f / (float)D;
     const int H = p.H, HD = D / H;
-    int nun[5], ubeg[5];
+    int nun[5], ubeg[5], ntl[5];
     for (int ph = 0; ph < 5; ++ph) {
         nun[ph] = ph_units(sd, ph, cta);
         ubeg[ph] = (int)col_begin(ph_N(sd, ph), cta, G);
+        ntl[ph] = (nun[ph] + UPT - 1) / UPT;
     }
-    const int n_red = D / 8;  // reducer CTAs of the mlp.c_proj partial sums (8 outputs each)
+    const int n_red = D / 8;  // reducer CTAs of the mlp.c_proj partial sums (8 outputs each, one per warp)
     const SampleCfg scfg{p.V, p.top_k, p.top_p, p.top_p_threshold, p.temperature, p.rep_penalty};
     int n = n_start;  // tokens emitted so far
     long long last_tok = st->last_tok[0];
@@ -645,6 +768,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     const float* mel_pos = p.blob + p.mel_pos_off;
     unsigned* const hc = p.hops;
     unsigned t_xq = 0, t_ao = 0, t_x1 = 0, t_pp = 0, t_x2 = 0, t_lg = 0;  // hop counter targets (counters are zero at launch)
+    float shift1 = 0.0f, shift2 = 0.0f;  // statistics shifts of ln_1 / ln_2: the means seen one layer earlier
 
     for (int i = 0; i < p.n_steps; ++i) {
         const bool tr = p.trace != nullptr && i == p.trace_step && tid == 0;
@@ -653,7 +777,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
             if (tr && slot < p.trace_slots) trow[slot] = globaltimer_ns();
         };
         stamp(p.L * GV_TRACE_PER_LAYER + 4);
-        float lat0 = 0.0f, lat1 = 0.0f;  // final_norm(ln_f(x)): the latent of this step (elements 2 tid, 2 tid + 1)
+        cs.wacc = tr ? &wait_ns : nullptr;
+        auto stamp_wait = [&](int slot) {  // stores the weight-wait time accumulated since the previous call
+            if (tr && slot < p.trace_slots) trow[slot] = wait_ns;
+            wait_ns = 0;
+        };
+        float4 lat = make_float4(0.f, 0.f, 0.f, 0.f);  // final_norm(ln_f(x)): the latent of this step (elements 4 tid ..)
         if (!(i == 0 && had_pending)) {
             // ------------- forward of token `last_tok` at mel position n, cache row P + n -------------
             const uint32_t tbase = p.tag0 + fwd * tags_per_fwd;
@@ -667,35 +796,32 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                 float* vc = p.kv + ((size_t)l * 2 + 1) * p.kv_layer_stride;
                 const uint32_t tg = tbase + (uint32_t)GV_TAGS_PER_LAYER * (uint32_t)l;
                 const int ts = l * GV_TRACE_PER_LAYER;
-                // ---- QKV: LN1 -> [q|k|v] columns ----
+                // ---- QKV: [q|k|v] = LN1(x) . W_attn + b  (LN folded: GEMV on raw x, statistics in the epilogue) ----
                 {
-                    float x0 = 0.0f, x1 = 0.0f;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (l == 0) {
                         if (xvalid) {
-                            const float2 a = *reinterpret_cast<const float2*>(mel_emb + (size_t)last_tok * D + 2 * tid);
-                            const float2 b = *reinterpret_cast<const float2*>(mel_pos + (size_t)n * D + 2 * tid);
-                            x0 = a.x + b.x;
-                            x1 = a.y + b.y;
+                            const float4 a = *reinterpret_cast<const float4*>(mel_emb + (size_t)last_tok * D + 4 * tid);
+                            const float4 b = *reinterpret_cast<const float4*>(mel_pos + (size_t)n * D + 4 * tid);
+                            x = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
                         }
                     } else {
                         hop_wait(hc + HC_X2 * GV_HOP_STRIDE, t_x2, tid, tmask);
-                        if (xvalid) {
-                            const float2 v = ld_tagged2(p.x2, 2 * tid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask);
-                            x0 = v.x;
-                            x1 = v.y;
-                        }
+                        if (xvalid) ld_tagged_vec<4>(p.x2, 4 * tid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask, &x.x);
                     }
-                    if (xvalid) *reinterpret_cast<float2*>(xres0 + 2 * tid) = make_float2(x0, x1);
+                    if (xvalid) *reinterpret_cast<float4*>(xres0 + 4 * tid) = x;
                     stamp(ts + 0);
-                    tile_wait(ring, cs);
-                    const float* lnp = tile_ptr(ring, cs);
-                    ln_pair(x0, x1, xvalid, D, lnp, lnp + D, red, tid);
-                    tile_release(ring, cs, lane);
-                    if (xvalid) *reinterpret_cast<float2*>(xn + 2 * tid) = make_float2(x0, x1);
+                    stats_partial(x, xvalid, shift1, red, lane, warp);
                     bar_sync(1, MEGA_CONSUMERS);
-                    gemv_dot<NXV>(ring, cs, nun[PH_QKV], xn, warp, lane,
-                                  [&](int u, float y) { st_tagged(p.xq, ubeg[PH_QKV] + u, y, tg + TG_XQ); });
+                    float mean, rstd;
+                    stats_finish(red, inv_d, shift1, mean, rstd);
+                    shift1 = mean;
                     stamp(ts + 1);
+                    gemv_dot<NXV>(ring, cs, nun[PH_QKV], xres0, warp, lane, [&](int u, float dot, float c2, float c1) {
+                        st_tagged(p.xq, ubeg[PH_QKV] + u, fmaf(rstd, fmaf(-mean, c1, dot), c2), tg + TG_XQ);
+                    });
+                    cs.gt += (uint32_t)ntl[PH_QKV];
+                    stamp(ts + 2);
                     hop_arrive(hc + HC_XQ * GV_HOP_STRIDE, tid);
                     t_xq += (unsigned)G;
                 }
@@ -707,7 +833,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     float* vh = vc + (size_t)h * p.S_max * HD;
 #define GV_ATT_CASE(hd)                                                                                                     \
     case hd:                                                                                                                \
-        att_item<hd>(kh, vh, p.xq, D, h, j0, j1, S, tg + TG_XQ, hc + HC_XQ * GV_HOP_STRIDE, t_xq, att_so, att_sml, tid,     \
+        att_item<hd>(kh, vh, p.xq, D, h, j0, j1, S, tg + TG_XQ, hc + HC_XQ * GV_HOP_STRIDE, t_xq, att_sc, att_op, tid,      \
                      p.att_o, p.att_ml, cta, tg + TG_AO, tmask);                                                            \
         break;
                     switch (HD) {
@@ -718,79 +844,133 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     hop_arrive(hc + HC_AO * GV_HOP_STRIDE, tid);
                 }
                 t_ao += (unsigned)n_items;
-                stamp(ts + 2);
+                stamp(ts + 3);
                 // ---- PROJ: merge attention partials -> o ; x1 = x + o . W_proj + b ----
                 {
                     hop_wait(hc + HC_AO * GV_HOP_STRIDE, t_ao, tid, tmask);
-                    float o0 = 0.0f, o1 = 0.0f;
                     if (xvalid) {
-                        const int h = (2 * tid) / HD, d = (2 * tid) % HD;
-                        float M = -INFINITY, den = 0.0f;
-                        for (int s2 = 0; s2 < nsplit; ++s2) {  // running merge in split order
-                            const int it = h * nsplit + s2;
-                            const float2 ml = ld_tagged2(p.att_ml, it * 2, tg + TG_AO, tmask);
-                            const float2 ov = ld_tagged2(p.att_o, it * HD + d, tg + TG_AO, tmask);
-                            const float Mn = fmaxf(M, ml.x);
-                            const float c_old = expf(M - Mn);  // first split: exp(-inf) = 0
-                            const float c_new = expf(ml.x - Mn);
-                            den = den * c_old + ml.y * c_new;
-                            o0 = o0 * c_old + ov.x * c_new;
-                            o1 = o1 * c_old + ov.y * c_new;
-                            M = Mn;
+                        const int h = (4 * tid) / HD, d = (4 * tid) % HD;
+                        const uint32_t tga = tg + TG_AO;
+                        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, M = -INFINITY, den = 0.0f;
+                        for (int s0 = 0; s0 < nsplit; s0 += 4) {  // loads of four splits in flight, merged in split order
+                            uint4 a[4], b[4], c[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (s0 + q < nsplit) {
+                                    const int it = h * nsplit + s0 + q;
+                                    a[q] = ld_x16(p.att_ml + 2 * (size_t)(it * 2));
+                                    b[q] = ld_x16(p.att_o + 2 * (size_t)(it * HD + d));
+                                    c[q] = ld_x16(p.att_o + 2 * (size_t)(it * HD + d + 2));
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (s0 + q < nsplit) {
+                                    const int it = h * nsplit + s0 + q;
+                                    uint32_t spins = 0;
+                                    while (!(tags_ok(a[q], tga, tmask) && tags_ok(b[q], tga, tmask) && tags_ok(c[q], tga, tmask))) {
+                                        if (++spins > MEGA_SPIN_LIMIT) __trap();
+                                        a[q] = ld_x16(p.att_ml + 2 * (size_t)(it * 2));
+                                        b[q] = ld_x16(p.att_o + 2 * (size_t)(it * HD + d));
+                                        c[q] = ld_x16(p.att_o + 2 * (size_t)(it * HD + d + 2));
+                                    }
+                                    const float mq = __uint_as_float(a[q].x), lq = __uint_as_float(a[q].z);
+                                    const float Mn = fmaxf(M, mq);
+                                    const float c_old = expf(M - Mn);  // first split: exp(-inf) = 0
+                                    const float c_new = expf(mq - Mn);
+                                    den = den * c_old + lq * c_new;
+                                    o0 = o0 * c_old + __uint_as_float(b[q].x) * c_new;
+                                    o1 = o1 * c_old + __uint_as_float(b[q].z) * c_new;
+                                    o2 = o2 * c_old + __uint_as_float(c[q].x) * c_new;
+                                    o3 = o3 * c_old + __uint_as_float(c[q].z) * c_new;
+                                    M = Mn;
+                                }
+                            }
                         }
-                        o0 = o0 / den;
-                        o1 = o1 / den;
-                        *reinterpret_cast<float2*>(xn + 2 * tid) = make_float2(o0, o1);
+                        *reinterpret_cast<float4*>(xo + 4 * tid) = make_float4(o0 / den, o1 / den, o2 / den, o3 / den);
                     }
-                    stamp(ts + 3);
-                    bar_sync(1, MEGA_CONSUMERS);
-                    gemv_dot<NXV>(ring, cs, nun[PH_PROJ], xn, warp, lane, [&](int u, float y) {
-                        const int col = ubeg[PH_PROJ] + u;
-                        st_tagged(p.x1, col, xres0[col] + y, tg + TG_X1);
-                    });
                     stamp(ts + 4);
+                    bar_sync(1, MEGA_CONSUMERS);
+                    gemv_dot<NXV>(ring, cs, nun[PH_PROJ], xo, warp, lane, [&](int u, float dot, float c2, float) {
+                        const int col = ubeg[PH_PROJ] + u;
+                        st_tagged(p.x1, col, xres0[col] + (dot + c2), tg + TG_X1);
+                    });
+                    cs.gt += (uint32_t)ntl[PH_PROJ];
+                    stamp(ts + 5);
+                    stamp_wait(ts + 12);
                     hop_arrive(hc + HC_X1 * GV_HOP_STRIDE, tid);
                     t_x1 += (unsigned)G;
                 }
-                // ---- FC + P2: LN2 -> u = gelu_new(. W_fc + b) (kept in this CTA) -> partial of u . W_proj2 ----
+                // ---- FC + P2: u = gelu_new(LN2(x1) . W_fc + b) (kept in this CTA) -> partial of u . W_proj2 ----
                 {
                     hop_wait(hc + HC_X1 * GV_HOP_STRIDE, t_x1, tid, tmask);
-                    float x0 = 0.0f, x1 = 0.0f;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (xvalid) {
-                        const float2 v = ld_tagged2(p.x1, 2 * tid, tg + TG_X1, tmask);
-                        x0 = v.x;
-                        x1 = v.y;
-                        *reinterpret_cast<float2*>(xres1 + 2 * tid) = v;
+                        ld_tagged_vec<4>(p.x1, 4 * tid, tg + TG_X1, tmask, &x.x);
+                        *reinterpret_cast<float4*>(xres1 + 4 * tid) = x;
                     }
-                    stamp(ts + 5);
-                    tile_wait(ring, cs);
-                    const float* lnp = tile_ptr(ring, cs);
-                    ln_pair(x0, x1, xvalid, D, lnp, lnp + D, red, tid);
-                    tile_release(ring, cs, lane);
-                    if (xvalid) *reinterpret_cast<float2*>(xn + 2 * tid) = make_float2(x0, x1);
-                    bar_sync(1, MEGA_CONSUMERS);
-                    gemv_dot<NXV>(ring, cs, nun[PH_FC], xn, warp, lane, [&](int u, float y) { us[u] = gelu_new(y); });
-                    bar_sync(1, MEGA_CONSUMERS);
-                    float acc0 = 0.0f, acc1 = 0.0f;
-                    gemv_outer<NXV>(ring, cs, nun[PH_P2], us, tid, lane, acc0, acc1);
-                    if (xvalid) st_tagged2(p.pp, cta * D + 2 * tid, acc0, acc1, tg + TG_PP);
                     stamp(ts + 6);
+                    stats_partial(x, xvalid, shift2, red + 16, lane, warp);
+                    bar_sync(1, MEGA_CONSUMERS);
+                    float mean, rstd;
+                    stats_finish(red + 16, inv_d, shift2, mean, rstd);
+                    shift2 = mean;
+                    stamp(ts + 7);
+                    gemv_dot<NXV>(ring, cs, nun[PH_FC], xres1, warp, lane, [&](int u, float dot, float c2, float c1) {
+                        us[u] = gelu_new(fmaf(rstd, fmaf(-mean, c1, dot), c2));
+                    });
+                    cs.gt += (uint32_t)ntl[PH_FC];
+                    bar_sync(1, MEGA_CONSUMERS);
+                    stamp(ts + 8);
+                    gemv_outer<NXV>(ring, cs, nun[PH_P2], us, tid, lane, warp, part);
+                    cs.gt += (uint32_t)ntl[PH_P2];
+                    bar_sync(1, MEGA_CONSUMERS);
+                    if (xvalid) {
+                        const float4 p0 = *reinterpret_cast<const float4*>(part + 4 * tid);
+                        const float4 p1 = *reinterpret_cast<const float4*>(part + D + 4 * tid);
+                        st_tagged2(p.pp, cta * D + 4 * tid, p0.x + p1.x, p0.y + p1.y, tg + TG_PP);
+                        st_tagged2(p.pp, cta * D + 4 * tid + 2, p0.z + p1.z, p0.w + p1.w, tg + TG_PP);
+                    }
+                    stamp(ts + 9);
+                    stamp_wait(ts + 13);
                     hop_arrive(hc + HC_PP * GV_HOP_STRIDE, tid);
                     t_pp += (unsigned)G;
                 }
                 // ---- RED: x2 = x1 + b + sum over CTAs of the partials (8 outputs per reducer CTA) ----
                 if (cta < n_red) {
                     float b2 = 0.0f;
-                    if (warp < 8 && lane == 0) b2 = __ldg(p.blob + p.proj2_b_off + (long long)l * p.layer_stride + cta * 8 + warp);
+                    if (lane == 0) b2 = __ldg(p.blob + p.proj2_b_off + (long long)l * p.layer_stride + cta * 8 + warp);
                     hop_wait(hc + HC_PP * GV_HOP_STRIDE, t_pp, tid, tmask);
-                    stamp(ts + 7);
-                    for (int q = tid; q < G * 4; q += MEGA_CONSUMERS) {
-                        const int c = q >> 2, part = q & 3;
-                        const float2 v = ld_tagged2(p.pp, c * D + cta * 8 + 2 * part, tg + TG_PP, tmask);
-                        *reinterpret_cast<float2*>(gat + c * 8 + 2 * part) = v;
+                    stamp(ts + 10);
+                    {   // load q: 16 bytes {v, tag, v, tag} of source CTA q / 4, outputs 2 (q % 4), +1; three rounds in flight
+                        const uint32_t tgp = tg + TG_PP;
+                        const int nq = G * 4;
+                        uint4 a[3];
+                        const float* ap[3];
+#pragma unroll
+                        for (int rr = 0; rr < 3; ++rr) {
+                            const int q = tid + rr * MEGA_CONSUMERS;
+                            ap[rr] = p.pp + 2 * (size_t)((q < nq ? (q >> 2) : 0) * D + cta * 8 + 2 * (q & 3));
+                            a[rr] = make_uint4(0u, tgp, 0u, tgp);
+                            if (q < nq) a[rr] = ld_x16(ap[rr]);
+                        }
+                        uint32_t spins = 0;
+                        while (!(tags_ok(a[0], tgp, tmask) && tags_ok(a[1], tgp, tmask) && tags_ok(a[2], tgp, tmask))) {
+                            if (++spins > MEGA_SPIN_LIMIT) __trap();
+#pragma unroll
+                            for (int rr = 0; rr < 3; ++rr)
+                                if (tid + rr * MEGA_CONSUMERS < nq) a[rr] = ld_x16(ap[rr]);
+                        }
+#pragma unroll
+                        for (int rr = 0; rr < 3; ++rr) {
+                            const int q = tid + rr * MEGA_CONSUMERS;
+                            if (q < nq)
+                                *reinterpret_cast<float2*>(gat + (q >> 2) * 8 + 2 * (q & 3)) =
+                                    make_float2(__uint_as_float(a[rr].x), __uint_as_float(a[rr].z));
+                        }
                     }
                     bar_sync(1, MEGA_CONSUMERS);
-                    if (warp < 8) {
+                    {
                         float s = 0.0f;
                         for (int c = lane; c < G; c += 32) s += gat[c * 8 + warp];
                         s = warp_sum(s);
@@ -799,7 +979,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                             st_tagged(p.x2, col, (xres1[col] + b2) + s, tg + TG_X2);
                         }
                     }
-                    stamp(ts + 8);
+                    stamp(ts + 11);
                     hop_arrive(hc + HC_X2 * GV_HOP_STRIDE, tid);
                 }
                 t_x2 += (unsigned)n_red;
@@ -809,22 +989,19 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                 const uint32_t tg = tbase + (uint32_t)GV_TAGS_PER_LAYER * (uint32_t)p.L;
                 const int ts = p.L * GV_TRACE_PER_LAYER;
                 hop_wait(hc + HC_X2 * GV_HOP_STRIDE, t_x2, tid, tmask);
-                if (xvalid) {
-                    const float2 v = ld_tagged2(p.x2, 2 * tid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask);
-                    lat0 = v.x;
-                    lat1 = v.y;
-                }
+                if (xvalid) ld_tagged_vec<4>(p.x2, 4 * tid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask, &lat.x);
                 stamp(ts + 0);
-                tile_wait(ring, cs);
-                const float* lnp = tile_ptr(ring, cs);
-                ln_pair(lat0, lat1, xvalid, D, lnp, lnp + D, red, tid);
+                const float* lnp = tile_wait(ring, cs, cs.gt, lane);  // all warps read the parameter tile
+                ln_quad(lat, xvalid, D, lnp, lnp + D, red, tid);
                 bar_sync(1, MEGA_CONSUMERS);  // `red` is reused by the second LayerNorm
-                ln_pair(lat0, lat1, xvalid, D, lnp + 2 * D, lnp + 3 * D, red, tid);
-                tile_release(ring, cs, lane);
-                if (xvalid) *reinterpret_cast<float2*>(xn + 2 * tid) = make_float2(lat0, lat1);
+                ln_quad(lat, xvalid, D, lnp + 2 * D, lnp + 3 * D, red, tid);
+                if (xvalid) *reinterpret_cast<float4*>(xo + 4 * tid) = lat;
                 bar_sync(1, MEGA_CONSUMERS);
-                gemv_dot<NXV>(ring, cs, nun[PH_HEAD], xn, warp, lane,
-                              [&](int u, float y) { st_tagged(p.lg, ubeg[PH_HEAD] + u, y, tg); });
+                if (warp == 0) tile_release(ring, cs.gt, lane, 4u);
+                cs.gt += 1u;
+                gemv_dot<NXV>(ring, cs, nun[PH_HEAD], xo, warp, lane,
+                              [&](int u, float dot, float c2, float) { st_tagged(p.lg, ubeg[PH_HEAD] + u, dot + c2, tg); });
+                cs.gt += (uint32_t)ntl[PH_HEAD];
                 stamp(ts + 1);
                 hop_arrive(hc + HC_LG * GV_HOP_STRIDE, tid);
                 t_lg += (unsigned)G;
@@ -843,27 +1020,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
         } else {
             // logits / latent left pending by the prefill (per-op kernels; plain arrays)
             for (int e = tid; e < p.V; e += MEGA_CONSUMERS) slog[e] = ldcg(p.pend_logits + e);
-            if (xvalid) {
-                const float2 a = ldcg2(p.pend_latent + 2 * tid);
-                lat0 = a.x;
-                lat1 = a.y;
-            }
+            if (xvalid) lat = ldcg4(p.pend_latent + 4 * tid);
         }
         bar_sync(1, MEGA_CONSUMERS);  // slog complete; attention / gather scratch (aliasing `keys`) is dead
-        // ------------- sample + emit (every CTA computes the same token; warps 0-7 run the chain) -------------
-        if (tid < GV_SAMPLE_THREADS) {
-            const int t = sample_token([&](int e) { return slog[e]; }, seen, scfg, p.noise ? p.noise + (size_t)i * p.V : nullptr,
-                                       p.seed, (uint32_t)n, 0u, keys, fscr, iscr, tid, [] { bar_sync(2, GV_SAMPLE_THREADS); });
-            if (tid == 0) ctl[2] = t;
-        }
-        bar_sync(1, MEGA_CONSUMERS);
-        int tok = ctl[2];
+        // ------------- sample + emit (every CTA computes the same token) -------------
+        int tok = sample_token([&](int e) { return slog[e]; }, seen, scfg, p.noise ? p.noise + (size_t)i * p.V : nullptr, p.seed,
+                               (uint32_t)n, 0u, keys, fscr, iscr, tid, [] { bar_sync(1, MEGA_CONSUMERS); });
         stamp(p.L * GV_TRACE_PER_LAYER + 3);
         if (p.forced) tok = (int)p.forced[i];
         if (!p.ignore_eos && finished) tok = p.stop_token;
         if (cta == 0) {
             if (tid == 0) p.ids_out[i] = tok;
-            if (xvalid) *reinterpret_cast<float2*>(p.latents_out + (size_t)i * D + 2 * tid) = make_float2(lat0, lat1);
+            if (xvalid) *reinterpret_cast<float4*>(p.latents_out + (size_t)i * D + 4 * tid) = lat;
             if (p.logits_out)
                 for (int q = tid; q < p.V; q += MEGA_CONSUMERS) p.logits_out[(size_t)i * p.V + q] = slog[q];
         }
@@ -880,7 +1048,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     }
     // tell the producer to stop (it may be blocked on a full ring or still have copies in flight)
     if (tid == 0) {
-        ctl[1] = (int)cs.tiles;
+        ctl[1] = (int)cs.gt;
         __threadfence_block();
         ctl[0] = 1;
     }
@@ -908,7 +1076,7 @@ size_t mega_smem_bytes(int D, int Vpad) {
     off += MEGA_SCRATCH_BYTES;
     off += (size_t)Vpad * sizeof(float) + 3 * (size_t)D * sizeof(float);
     off += 32 * sizeof(uint64_t);
-    off += (32 + 32 + 16) * sizeof(float) + 16 * sizeof(int) + 4 * sizeof(int);
+    off += (32 + 64 + 16) * sizeof(float) + 16 * sizeof(int) + 4 * sizeof(int);
     off += Vpad;
     return (off + 15) & ~size_t(15);
 }

@@ -14,7 +14,7 @@ enum { HC_XQ = 0, HC_AO = 1, HC_X1 = 2, HC_PP = 3, HC_X2 = 4, HC_LG = 5, HC_COUN
 // exchange tags of one forward: tag(layer l, buffer b) = tbase + GV_TAGS_PER_LAYER*l + b; logits = tbase + GV_TAGS_PER_LAYER*L
 #define GV_TAGS_PER_LAYER 5
 // debug timeline slots per layer (genvc_debug_trace)
-#define GV_TRACE_PER_LAYER 10
+#define GV_TRACE_PER_LAYER 14
 
 struct MegaParams {
     int L, D, H, V, Vpad, S_max;
@@ -23,7 +23,7 @@ struct MegaParams {
     // weights
     const float* stream;  // per-CTA weight streams (stream_layout.h)
     const float* blob;    // reference-layout blob (LayerNorm params, biases, embeddings)
-    long long ln1_off, ln2_off, proj2_b_off, layer_stride, lnf_off, mel_emb_off, mel_pos_off;
+    long long proj2_b_off, layer_stride, lnf_off, mel_emb_off, mel_pos_off;
     // activations / state (global, L2-resident)
     float* kv;
     long long kv_layer_stride;  // floats per (layer, k|v) plane
@@ -64,6 +64,6 @@ struct MegaParams {
 size_t mega_smem_bytes(int D, int Vpad);
 cudaError_t launch_decode_mega(const MegaParams& p, int grid, cudaStream_t st);
 cudaError_t launch_pack_stream(const StreamDims& s, int layer, int ph, const float* W, const float* bias, int w_nk,
-                               float* stream, cudaStream_t st);
+                               const float* lnw, const float* lnb, float* stream, cudaStream_t st);
 
 }  // namespace gv

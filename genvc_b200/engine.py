@@ -265,7 +265,7 @@ class Engine:
             self._check(self.lib.genvc_debug_trace(self._ctx, None, 0, 0))
             self._trace = None
             return None
-        slots = self.dims.n_layer * 10 + 8
+        slots = self.dims.n_layer * 14 + 8
         g = self.decode_grid
         self._trace = torch.zeros(g * slots, dtype=torch.int64, device=self.device)
         self._check(self.lib.genvc_debug_trace(self._ctx, self._trace.data_ptr(), slots, int(step)))

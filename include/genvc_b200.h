@@ -169,11 +169,13 @@ uint64_t genvc_launch_count(const genvc_ctx* ctx);
 /* Debug/profiling hook (no reference counterpart): when trace_dev != NULL, thread 0 of
  * every persistent CTA of the fused decode kernel writes %globaltimer (ns) at each phase
  * boundary of step `step` of every following genvc_decode launch into
- * trace_dev[cta * slots_per_cta + slot]; slot = layer*10 + k with k = 0 QKV input ready,
- * 1 QKV done, 2 attention item done, 3 attention output merged, 4 PROJ done, 5 FC input ready,
- * 6 FC + mlp.c_proj partial done, 7 partial sums gathered (reducer CTAs), 8 reduce done;
- * n_layer*10 + {0,1,2,3,4} = head input ready, head done, logits gathered, sample done, step
- * start.  The buffer must hold grid * slots_per_cta words.  NULL switches it off. */
+ * trace_dev[cta * slots_per_cta + slot]; slot = layer*14 + k with k = 0 QKV input ready,
+ * 1 LN1 done, 2 QKV done, 3 attention item done, 4 attention output merged, 5 PROJ done, 6 FC
+ * input ready, 7 LN2 done, 8 FC done, 9 mlp.c_proj partial done, 10 partial sums gathered
+ * (reducer CTAs), 11 reduce done; k = 12, 13 are DURATIONS (ns thread 0 waited for weight tiles
+ * in QKV+PROJ and in FC+P2); n_layer*14 + {0,1,2,3,4} = head input ready, head done, logits
+ * gathered, sample done, step start.  The buffer must hold grid * slots_per_cta words.  NULL
+ * switches it off. */
 int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, int step);
 
 /* Tuning / debug knobs of the fused decode kernel (no reference counterpart):

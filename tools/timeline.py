@@ -17,11 +17,12 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-# trace slots per layer (include/genvc_b200.h): k = 0 QKV input ready, 1 QKV done, 2 ATT item done, 3 attention
-# output merged, 4 PROJ done, 5 FC input ready, 6 FC+P2 done, 7 partials gathered, 8 reduce done
+# trace slots per layer (include/genvc_b200.h)
+TPL = 14
 SEGMENTS = [
-    ("x2 hop + load", None, 0), ("LN1 + QKV gemv", 0, 1), ("attention item", 1, 2), ("AO hop + merge", 2, 3),
-    ("PROJ gemv", 3, 4), ("x1 hop + load", 4, 5), ("LN2 + FC + P2 gemv", 5, 6), ("PP hop", 6, 7), ("gather + reduce", 7, 8),
+    ("x2 hop + load", None, 0), ("LN1", 0, 1), ("QKV gemv", 1, 2), ("attention item", 2, 3), ("AO hop + merge", 3, 4),
+    ("PROJ gemv", 4, 5), ("x1 hop + load", 5, 6), ("LN2", 6, 7), ("FC gemv", 7, 8), ("P2 gemv", 8, 9), ("PP hop", 9, 10),
+    ("gather + reduce", 10, 11),
 ]
 
 
@@ -30,7 +31,7 @@ def analyse(tr: torch.Tensor, L: int) -> dict:
     (latest CTA) view: time between the latest stamp of the segment's end and the latest of its start."""
     tr = tr.cpu().double()  # [G, slots] ns
     G = tr.shape[0]
-    start = tr[:, L * 10 + 4]
+    start = tr[:, L * TPL + 4]
     t0 = float(start.min())
     out = {"grid": G, "segments": {}}
     acc = {name: {"med": [], "max": [], "crit": []} for name, _, _ in SEGMENTS}
@@ -39,11 +40,11 @@ def analyse(tr: torch.Tensor, L: int) -> dict:
             if a is None:
                 if l == 0:
                     continue
-                ta = tr[:, (l - 1) * 10 + 8]
-                ta = torch.where(ta > 0, ta, tr[:, (l - 1) * 10 + 6])  # non-reducer CTAs skip slots 7, 8
+                ta = tr[:, (l - 1) * TPL + 11]
+                ta = torch.where(ta > 0, ta, tr[:, (l - 1) * TPL + 9])  # non-reducer CTAs skip slots 10, 11
             else:
-                ta = tr[:, l * 10 + a]
-            tb = tr[:, l * 10 + b]
+                ta = tr[:, l * TPL + a]
+            tb = tr[:, l * TPL + b]
             ok = (ta > 0) & (tb > 0)
             if not ok.any():
                 continue
@@ -53,14 +54,17 @@ def analyse(tr: torch.Tensor, L: int) -> dict:
             acc[name]["crit"].append(float(tb[ok].max() - ta[ok].max()))
     for name, a in acc.items():
         out["segments"][name] = {k: round(statistics.mean(v), 1) if v else 0.0 for k, v in a.items()}
-    head = L * 10
+    head = L * TPL
+    ww = tr[:, : L * TPL].view(G, L, TPL)
+    out["weight_wait_ns"] = {"QKV+PROJ med": float(ww[:, :, 12].mean(1).median()), "QKV+PROJ max": float(ww[:, :, 12].mean(1).max()),
+                             "FC+P2 med": float(ww[:, :, 13].mean(1).median()), "FC+P2 max": float(ww[:, :, 13].mean(1).max())}
     out["head"] = {
-        "x2 hop + load": float((tr[:, head + 0] - torch.where(tr[:, head - 2] > 0, tr[:, head - 2], tr[:, head - 4])).median()),
+        "x2 hop + load": float((tr[:, head + 0] - torch.where(tr[:, head - 3] > 0, tr[:, head - 3], tr[:, head - 5])).median()),
         "2xLN + head gemv": float((tr[:, head + 1] - tr[:, head + 0]).median()),
         "logits hop + load": float((tr[:, head + 2] - tr[:, head + 1]).median()),
         "sample": float((tr[:, head + 3] - tr[:, head + 2]).median()),
     }
-    out["layer_ns"] = float((tr[:, (L - 1) * 10 + 6].max() - tr[:, 0].max()) / max(L - 1, 1)) if L > 1 else 0.0
+    out["layer_ns"] = float((tr[:, (L - 1) * TPL].max() - tr[:, 0].max()) / max(L - 1, 1)) if L > 1 else 0.0
     out["step_ns"] = float(tr[:, head + 3].max() - t0)
     return out
 
@@ -115,6 +119,7 @@ def main():
         for name, a in v["segments"].items():
             print(f"  {name:20s} med {a['med']/1e3:6.2f} us  max {a['max']/1e3:6.2f}  critical-path {a['crit']/1e3:6.2f}")
         print("  head:", {n: round(x / 1e3, 2) for n, x in v["head"].items()})
+        print("  weight wait per layer (thread 0):", {n: round(x / 1e3, 2) for n, x in v["weight_wait_ns"].items()})
 
 
 if __name__ == "__main__":
