@@ -64,7 +64,7 @@ struct genvc_ctx {
     // debug timeline of the fused decode kernel (genvc_debug_trace)
     unsigned long long* trace = nullptr;
     int trace_slots = 0, trace_step = 0;
-    int window = 4, dbg_nosync = 0;
+    int window = 4, dbg_nosync = 0, l2_ahead = 0;
 
     // host mirror of the generation state
     int B = 0, P = 0;
@@ -291,9 +291,10 @@ int genvc_bind_buffers(genvc_ctx* ctx, float* kv_dev, uint64_t kv_floats, void* 
 
 uint64_t genvc_launch_count(const genvc_ctx* ctx) { return ctx ? ctx->nlaunch : 0; }
 
-int genvc_debug_tune(genvc_ctx* ctx, int window, int nosync) {
+int genvc_debug_tune(genvc_ctx* ctx, int window, int nosync, int l2_ahead_tiles) {
     if (!ctx) return GENVC_E_INVALID;
     if (window > 0) ctx->window = std::min(window, (int)GV_MEGA_NSLOT);
+    if (l2_ahead_tiles >= 0) ctx->l2_ahead = l2_ahead_tiles;
     ctx->dbg_nosync = nosync ? 1 : 0;
     return GENVC_OK;
 }
@@ -557,7 +558,7 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         p.ids_out = reinterpret_cast<long long*>(ids_out_dev); p.latents_out = latents_out_dev; p.logits_out = logits_out_dev;
         p.status = status_dev;
         p.trace = ctx->trace; p.trace_slots = ctx->trace_slots; p.trace_step = ctx->trace_step;
-        p.window = ctx->window; p.dbg_nosync = ctx->dbg_nosync;
+        p.window = ctx->window; p.dbg_nosync = ctx->dbg_nosync; p.l2_ahead_tiles = ctx->l2_ahead;
         CK(launch_decode_mega(p, ctx->grid, st));
         ctx->nlaunch += 1;
         ctx->n_host = std::min(max_total, ctx->n_host + n_steps);

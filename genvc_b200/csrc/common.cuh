@@ -116,6 +116,11 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_s
         : "memory");
 }
 
+// global -> L2 prefetch of a contiguous range (no completion tracking; bytes % 16 == 0)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // gpu-scope acquire/release on a global counter (grid barrier)
 // ---------------------------------------------------------------------------------------------

@@ -54,8 +54,35 @@ struct Ring {
     float* slots;
     uint64_t* full;
     uint64_t* empty;
+    uint32_t* landed;  // number of leading tiles the producer has SEEN complete (monotonic hint for the consumers)
     int slot_floats;
 };
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Tile `idx` is ready: either the producer already saw its full barrier complete (one shared-memory load,
+// the common case: tiles are requested microseconds ahead) or this thread waits on the barrier itself
+// (mbarrier.try_wait costs several hundred cycles even when the phase is long complete).
+__device__ __forceinline__ void tile_ready_wait(const Ring& r, uint32_t idx) {
+    if (ld_acquire_cta_shared(r.landed) > idx) return;
+    mbar_wait(&r.full[idx % NSLOT], (idx / NSLOT) & 1u);
+}
 
 // ---------------------------------------------------------------------------------------------
 // stream packing (init time): gather the reference-layout matrices into the per-CTA streams.
@@ -231,20 +258,42 @@ struct Cons {
     uint32_t gt;               // global index of the first tile of the current phase (same in every thread)
     unsigned long long* wacc;  // debug: accumulates ns spent waiting for weight tiles (null = off)
 };
-// One elected lane waits on the tile's full barrier; __syncwarp orders the other lanes behind it.
+__device__ __forceinline__ const float* slot_ptr(const Ring& r, uint32_t idx) {
+    return r.slots + (size_t)(idx % NSLOT) * r.slot_floats;
+}
+// Wait for all tiles t = g, g + 2, g + 4, g + 6 (< ntiles) of this warp's group at once: lane k waits
+// for tile g + 2k (32 lanes polling one mbarrier would serialise), __syncwarp orders the rest.
+__device__ __forceinline__ void group_wait(const Ring& r, const Cons& cs, int g, int ntiles, int lane) {
+    long long t0 = 0;
+    if (cs.wacc != nullptr && lane == 0) t0 = clock64();  // debug timeline
+    if (lane < 4) {
+        const int t = g + 2 * lane;
+        if (t < ntiles) tile_ready_wait(r, cs.gt + (uint32_t)t);
+    }
+    __syncwarp();
+    if (cs.wacc != nullptr && lane == 0) *cs.wacc += (unsigned long long)(clock64() - t0);
+}
+// Release them (this warp's arrival on each tile's empty barrier) once the warp has read its units.
+__device__ __forceinline__ void group_release(const Ring& r, const Cons& cs, int g, int ntiles, int lane) {
+    __syncwarp();
+    if (lane < 4) {
+        const int t = g + 2 * lane;
+        if (t < ntiles) mbar_arrive(&r.empty[(cs.gt + (uint32_t)t) % NSLOT]);
+    }
+}
+// single tile read by all warps (logits-head LayerNorm parameters)
 __device__ __forceinline__ const float* tile_wait(const Ring& r, const Cons& cs, uint32_t idx, int lane) {
-    const uint32_t slot = idx % NSLOT, par = (idx / NSLOT) & 1u;
     if (lane == 0) {
         if (cs.wacc != nullptr) {  // debug timeline
-            const unsigned long long t0 = globaltimer_ns();
-            mbar_wait(&r.full[slot], par);
-            *cs.wacc += globaltimer_ns() - t0;
+            const long long t0 = clock64();
+            tile_ready_wait(r, idx);
+            *cs.wacc += (unsigned long long)(clock64() - t0);
         } else {
-            mbar_wait(&r.full[slot], par);
+            tile_ready_wait(r, idx);
         }
     }
     __syncwarp();
-    return r.slots + (size_t)slot * r.slot_floats;
+    return slot_ptr(r, idx);
 }
 __device__ __forceinline__ void tile_release(const Ring& r, uint32_t idx, int lane, uint32_t count = 1u) {
     __syncwarp();
@@ -335,27 +384,25 @@ __device__ __forceinline__ void gemv_dot(const Ring& ring, const Cons& cs, int n
     for (int k = 0; k < 4; ++k) cc[k] = make_float2(0.f, 0.f);
     const int ntiles = (nunits + UPT - 1) / UPT;
     const int g = warp >> 2, r = warp & 3;
+    group_wait(ring, cs, g, ntiles, lane);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int t = g + 2 * k;
-        if (t < ntiles) {
-            const uint32_t idx = cs.gt + (uint32_t)t;
-            if (t * UPT + r < nunits) {
-                const float* col = tile_wait(ring, cs, idx, lane) + r * UF;
-                cc[k] = *reinterpret_cast<const float2*>(col + D);
-                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        if (t * UPT + r < nunits) {
+            const float* col = slot_ptr(ring, cs.gt + (uint32_t)t) + r * UF;
+            cc[k] = *reinterpret_cast<const float2*>(col + D);
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
-                for (int i = 0; i < NXV; ++i) {
-                    const float4 wv = *reinterpret_cast<const float4*>(col + (i * 32 + lane) * 4);
-                    a0 = fmaf(wv.x, xv[i].x, a0);
-                    a1 = fmaf(wv.y, xv[i].y, a1);
-                    a2 = fmaf(wv.z, xv[i].z, a2);
-                    a3 = fmaf(wv.w, xv[i].w, a3);
-                }
-                tot[k] = (a0 + a1) + (a2 + a3);
+            for (int i = 0; i < NXV; ++i) {
+                const float4 wv = *reinterpret_cast<const float4*>(col + (i * 32 + lane) * 4);
+                a0 = fmaf(wv.x, xv[i].x, a0);
+                a1 = fmaf(wv.y, xv[i].y, a1);
+                a2 = fmaf(wv.z, xv[i].z, a2);
+                a3 = fmaf(wv.w, xv[i].w, a3);
             }
-            tile_release(ring, idx, lane);
+            tot[k] = (a0 + a1) + (a2 + a3);
         }
+        if (t < ntiles) tile_release(ring, cs.gt + (uint32_t)t, lane);  // early: the producer refills while we go on
     }
     // transposing butterfly: lanes [8q, 8q+8) end up reducing tot[q]
     const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
@@ -389,8 +436,7 @@ __device__ __forceinline__ void gemv_outer(const Ring& ring, const Cons& cs, int
     for (int k = 0; k < 4; ++k) {
         const int t = g + 2 * k;
         if (t < ntiles) {
-            const uint32_t idx = cs.gt + (uint32_t)t;
-            const float* base = tile_wait(ring, cs, idx, lane) + 4 * j;
+            const float* base = tile_wait(ring, cs, cs.gt + (uint32_t)t, lane) + 4 * j;
 #pragma unroll
             for (int r = 0; r < UPT; ++r) {
                 const int kk = t * UPT + r;
@@ -404,8 +450,8 @@ __device__ __forceinline__ void gemv_outer(const Ring& ring, const Cons& cs, int
                     acc1.z = fmaf(uk, w1.z, acc1.z); acc1.w = fmaf(uk, w1.w, acc1.w);
                 }
             }
-            tile_release(ring, idx, lane);
         }
+        if (t < ntiles) tile_release(ring, cs.gt + (uint32_t)t, lane);
     }
     if (valid) {
         *reinterpret_cast<float4*>(part + g * D + 4 * j) = acc0;
@@ -455,15 +501,18 @@ __device__ __forceinline__ void st_vec(float* p, const float* r) {
 }
 
 template <int HD>
-__device__ void att_item(float* __restrict__ Kc, float* __restrict__ Vc, const float* xq, int D, int h, int j0, int j1, int S,
+__device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict__ Vc, const float* xq, int D, int h, int j0, int j1, int S,
                          uint32_t tag_in, const unsigned* cnt_in, unsigned target_in, float* sc, float* opart, int tid,
-                         float* o_out, float* ml_out, int item, uint32_t tag_out, uint32_t tmask) {
+                         float* o_out, float* ml_out, int item, uint32_t tag_out, uint32_t tmask, unsigned long long* dbg) {
     using L = AttLane<HD>;
+    long long ck[8];
+    ck[0] = clock64();
     constexpr int VEC = L::VEC, NCH = L::NCH, DPL = L::DPL;
-    constexpr int NS = MEGA_CONSUMERS / HD;  // key slices of the PV stage
-    constexpr int VPRE = 32 / NS;            // V elements per thread per 32-key block
+    constexpr int DV = HD / 4;               // PV stage: a thread owns 4 consecutive dims, DV threads cover a key
+    constexpr int NS = MEGA_CONSUMERS / DV;  // key slices of the PV stage
+    constexpr int VPRE = 32 / NS;            // V rows (float4) per thread per 32-key block
     const int warp = tid >> 5, lane = tid & 31;
-    const int ks = tid / HD, d = tid % HD;
+    const int ks = tid / DV, d = (tid % DV) * 4;
     const int nk = j1 - j0;
     const int jn = S - 1 - j0;  // relative index of the position being decoded (inside this item iff 0 <= jn < nk)
     const float sqrt_hd = sqrtf((float)HD);
@@ -477,32 +526,79 @@ __device__ void att_item(float* __restrict__ Kc, float* __restrict__ Vc, const f
             for (int i = 0; i < DPL; ++i) dst[i] = 0.0f;
         }
     };
-    auto load_v = [&](int jr) -> float { return (jr < nk && jr != jn) ? ldcg(Vc + (size_t)(j0 + jr) * HD + d) : 0.0f; };
+    auto load_v = [&](int jr) -> float4 {
+        return (jr < nk && jr != jn) ? ldcg4(Vc + (size_t)(j0 + jr) * HD + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
 
     // ---- prefetch block 0 from the cache (independent of this step's q) ----
-    float kr[ATT_ROWS][DPL], vr[VPRE];
+    float kr[ATT_ROWS][DPL];
+    float4 vr[VPRE];
 #pragma unroll
     for (int u = 0; u < ATT_ROWS; ++u) load_k_row(warp + MEGA_WARPS * u, kr[u]);
 #pragma unroll
     for (int i = 0; i < VPRE; ++i) vr[i] = load_v(ks + NS * i);
+    ck[1] = clock64();
     hop_wait(cnt_in, target_in, tid, tmask);
-    // ---- this step's q, and k / v of the position being decoded ----
-    float qr[DPL];
+    ck[2] = clock64();
+    // ---- this step's q, and k / v of the position being decoded: every tagged load in flight at once ----
+    float qr[DPL], knew[DPL];
+    float4 vnew = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool v_mine = jn >= 0 && jn < nk && (jn % NS) == ks;          // this thread's key slice contains the new position
+    const bool k_mine = jn >= 0 && jn < nk && (jn % MEGA_WARPS) == warp;  // this warp scores the new position
+    {
+        constexpr int NW16 = (DPL + 1) / 2;  // 16-byte words ({v, tag, v, tag}) per lane for HD floats ... 8-byte for DPL == 1
+        const float* qp = xq + 2 * (size_t)(h * HD);
+        const float* kp = xq + 2 * (size_t)(D + h * HD);
+        const float* vp = xq + 2 * (size_t)(2 * D + h * HD + d);  // 4 consecutive elements: two 16-byte words
+        uint32_t spins = 0;
+        bool ok = false;
+        while (!ok) {
+            ok = true;
+            if constexpr (DPL == 1) {
+                const uint2 a = ld_x8(qp + 2 * lane);
+                ok = ((a.y ^ tag_in) & tmask) == 0u;
+                qr[0] = __uint_as_float(a.x);
+                if (k_mine) {
+                    const uint2 b = ld_x8(kp + 2 * lane);
+                    ok = ok && ((b.y ^ tag_in) & tmask) == 0u;
+                    knew[0] = __uint_as_float(b.x);
+                }
+            } else {
+                uint4 a[NW16], b[NW16];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) ld_tagged_vec<VEC>(xq, h * HD + (c * 32 + lane) * VEC, tag_in, tmask, qr + c * VEC);
-    float vnew = 0.0f;
-    const bool v_mine = jn >= 0 && jn < nk && (jn % NS) == ks;  // this thread's key slice contains the new position
-    if (v_mine) {
-        vnew = ld_tagged1(xq, 2 * D + h * HD + d, tag_in, tmask);
-        __stcg(Vc + (size_t)(S - 1) * HD + d, vnew);
-    }
-    auto new_k_row = [&](float* dst) {
+                for (int c = 0; c < NCH; ++c)
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            ld_tagged_vec<VEC>(xq, D + h * HD + (c * 32 + lane) * VEC, tag_in, tmask, dst + c * VEC);
-            st_vec<VEC>(Kc + (size_t)(S - 1) * HD + (c * 32 + lane) * VEC, dst + c * VEC);
+                    for (int w2 = 0; w2 < VEC / 2; ++w2) {
+                        const int e = (c * 32 + lane) * VEC + 2 * w2;  // first of two consecutive elements
+                        a[c * (VEC / 2) + w2] = ld_x16(qp + 2 * e);
+                        if (k_mine) b[c * (VEC / 2) + w2] = ld_x16(kp + 2 * e);
+                    }
+#pragma unroll
+                for (int w2 = 0; w2 < NW16; ++w2) {
+                    ok = ok && tags_ok(a[w2], tag_in, tmask);
+                    qr[2 * w2] = __uint_as_float(a[w2].x);
+                    qr[2 * w2 + 1] = __uint_as_float(a[w2].z);
+                    if (k_mine) {
+                        ok = ok && tags_ok(b[w2], tag_in, tmask);
+                        knew[2 * w2] = __uint_as_float(b[w2].x);
+                        knew[2 * w2 + 1] = __uint_as_float(b[w2].z);
+                    }
+                }
+            }
+            if (v_mine) {
+                const uint4 v0 = ld_x16(vp), v1 = ld_x16(vp + 4);
+                ok = ok && tags_ok(v0, tag_in, tmask) && tags_ok(v1, tag_in, tmask);
+                vnew = make_float4(__uint_as_float(v0.x), __uint_as_float(v0.z), __uint_as_float(v1.x), __uint_as_float(v1.z));
+            }
+            if (++spins > MEGA_SPIN_LIMIT) __trap();
         }
-    };
+    }
+    ck[3] = clock64() + (long long)(qr[0] == 123.f);
+    if (v_mine) __stcg(reinterpret_cast<float4*>(Vc + (size_t)(S - 1) * HD + d), vnew);
+    if (k_mine) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) st_vec<VEC>(Kc + (size_t)(S - 1) * HD + (c * 32 + lane) * VEC, knew + c * VEC);
+    }
     // ---- scores ----
     for (int b = 0; b * 32 < nk; ++b) {
         if (b > 0) {
@@ -511,8 +607,10 @@ __device__ void att_item(float* __restrict__ Kc, float* __restrict__ Vc, const f
         }
 #pragma unroll
         for (int u = 0; u < ATT_ROWS; ++u) {
-            const int jr = b * 32 + warp + MEGA_WARPS * u;
-            if (jr == jn && jr < nk) new_k_row(kr[u]);
+            if (b * 32 + warp + MEGA_WARPS * u == jn && k_mine) {
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) kr[u][i] = knew[i];
+            }
         }
         float s[ATT_ROWS];
 #pragma unroll
@@ -533,27 +631,36 @@ __device__ void att_item(float* __restrict__ Kc, float* __restrict__ Vc, const f
         }
     }
     bar_sync(1, MEGA_CONSUMERS);
+    ck[4] = clock64();
     // ---- softmax weights (every warp, all keys) ----
     float pv[ATT_MAX_BLOCKS];
     float M = -INFINITY;
 #pragma unroll
     for (int b = 0; b < ATT_MAX_BLOCKS; ++b) {
-        pv[b] = (b * 32 + lane < nk) ? sc[b * 32 + lane] : -INFINITY;
-        M = fmaxf(M, pv[b]);
+        pv[b] = -INFINITY;
+        if (b * 32 < nk) {
+            if (b * 32 + lane < nk) pv[b] = sc[b * 32 + lane];
+            M = fmaxf(M, pv[b]);
+        }
     }
     M = warp_max(M);
     float Lsum = 0.0f;
 #pragma unroll
     for (int b = 0; b < ATT_MAX_BLOCKS; ++b) {
-        pv[b] = expf(pv[b] - M);  // outside the range: exp(-inf) = 0
-        Lsum += pv[b];
+        if (b * 32 < nk) {
+            pv[b] = expf(pv[b] - M);  // outside the range: exp(-inf) = 0
+            Lsum += pv[b];
+        } else {
+            pv[b] = 0.0f;
+        }
     }
     Lsum = warp_sum(Lsum);
+    ck[5] = clock64() + (long long)(Lsum == 123.f);
     // ---- PV ----
-    float o = 0.0f;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int b = 0; b < ATT_MAX_BLOCKS; ++b) {
-        if (b * 32 < nk) {  // warp-uniform
+        if (b * 32 < nk) {  // uniform
             if (b > 0) {
 #pragma unroll
                 for (int i = 0; i < VPRE; ++i) vr[i] = load_v(b * 32 + ks + NS * i);
@@ -561,24 +668,30 @@ __device__ void att_item(float* __restrict__ Kc, float* __restrict__ Vc, const f
 #pragma unroll
             for (int i = 0; i < VPRE; ++i) {
                 const int jr = b * 32 + ks + NS * i;
-                const float pj = __shfl_sync(0xffffffffu, pv[b], ks + NS * i);
-                const float vj = (jr == jn) ? vnew : vr[i];
-                o = fmaf(pj, vj, o);
+                const float pj = __shfl_sync(0xffffffffu, pv[b], (ks + NS * i) & 31);
+                const float4 vj = (jr == jn) ? vnew : vr[i];
+                o.x = fmaf(pj, vj.x, o.x);
+                o.y = fmaf(pj, vj.y, o.y);
+                o.z = fmaf(pj, vj.z, o.z);
+                o.w = fmaf(pj, vj.w, o.w);
             }
         }
     }
-    if constexpr (NS > 1) {
-        opart[ks * HD + d] = o;
-        bar_sync(1, MEGA_CONSUMERS);
-        if (tid < HD) {
-            o = 0.0f;
-#pragma unroll
-            for (int q = 0; q < NS; ++q) o += opart[q * HD + tid];
-        }
-    }
+    *reinterpret_cast<float4*>(opart + ks * HD + d) = o;
+    bar_sync(1, MEGA_CONSUMERS);
+    float os = 0.0f;
     if (tid < HD) {
-        st_tagged(o_out, item * HD + tid, o, tag_out);
+#pragma unroll
+        for (int q = 0; q < NS; ++q) os += opart[q * HD + tid];
+    }
+    ck[6] = clock64() + (long long)(os == 123.f);
+    if (tid < HD) {
+        st_tagged(o_out, item * HD + tid, os, tag_out);
         if (tid == 0) st_tagged2(ml_out, item * 2, M, Lsum, tag_out);
+    }
+    if (dbg != nullptr && tid == 0) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) dbg[q] = (unsigned long long)(ck[q + 1] - ck[q]);
     }
 }
 
@@ -587,32 +700,53 @@ __device__ void att_item(float* __restrict__ Kc, float* __restrict__ Vc, const f
 // ---------------------------------------------------------------------------------------------
 struct Producer {
     const Ring& ring;
+    const float* region = nullptr;   // this CTA's contiguous weight stream [region, region + region_floats)
+    long long region_floats = 0;
+    long long ahead_floats = 0;      // L2 prefetch distance (0 = off)
     uint32_t t = 0, slot = 0, phase = 0;
-    uint32_t window;  // at most this many tiles requested but not landed
+    uint32_t land = 0;  // tiles [0, land) have been seen complete (published to the consumers through ring.landed)
+    uint32_t window;    // at most this many tiles requested but not landed
     volatile int* stop;
     uint64_t policy;
     __device__ Producer(const Ring& r, volatile int* s, uint32_t w) : ring(r), window(w), stop(s) {
         policy = l2_policy_evict_first();
     }
+    // non-blocking: move `land` over every tile whose full barrier has completed and publish it
+    __device__ void advance() {
+        const uint32_t l0 = land;
+        while (land < t && mbar_test_wait(&ring.full[land % NSLOT], (land / NSLOT) & 1u)) ++land;
+        if (land != l0) st_release_cta_shared(ring.landed, land);
+    }
     // returns false when the consumers asked to stop
     __device__ bool issue(const float* src, uint32_t floats, bool stream_once) {
         uint32_t spins = 0;
-        while (!mbar_try_wait(&ring.empty[slot], phase ^ 1u)) {
+        while (!mbar_test_wait(&ring.empty[slot], phase ^ 1u)) {
+            advance();
             if (*stop) return false;
             if (++spins > MEGA_SPIN_LIMIT) __trap();
         }
         if (*stop) return false;
-        if (t >= window) {  // tile t - window must have landed
-            const uint32_t o = t - window;
-            spins = 0;
-            while (!mbar_try_wait(&ring.full[o % NSLOT], (o / NSLOT) & 1u)) {
-                if (++spins > MEGA_SPIN_LIMIT) __trap();
-            }
+        spins = 0;
+        while (t - land >= window) {  // at most `window` tiles requested but not landed
+            advance();
+            if (++spins > MEGA_SPIN_LIMIT) __trap();
         }
         mbar_arrive_expect_tx(&ring.full[slot], floats * 4u);
         float* dst = ring.slots + (size_t)slot * ring.slot_floats;
-        if (stream_once) bulk_g2s_hint(dst, src, floats * 4u, &ring.full[slot], policy);
-        else bulk_g2s(dst, src, floats * 4u, &ring.full[slot]);
+        if (stream_once) {
+            bulk_g2s_hint(dst, src, floats * 4u, &ring.full[slot], policy);
+            if (ahead_floats > 0) {
+                // HBM -> L2 for the bytes this CTA will want `ahead_floats` later (wraps to the next token's pass):
+                // the smem ring then refills at L2 latency, and HBM streaming no longer depends on ring depth
+                long long o = (src - region) + ahead_floats;
+                if (o >= region_floats) o -= region_floats;
+                const long long n = min((long long)floats, region_floats - o);
+                bulk_prefetch_l2(region + o, (uint32_t)n * 4u);
+                if (n < (long long)floats) bulk_prefetch_l2(region, (uint32_t)((long long)floats - n) * 4u);
+            }
+        } else {
+            bulk_g2s(dst, src, floats * 4u, &ring.full[slot]);
+        }
         ++t;
         if (++slot == NSLOT) {
             slot = 0;
@@ -649,7 +783,7 @@ __device__ bool produce_forward(Producer& pr, const MegaParams& p, const StreamD
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int NXV>
+template <int NXV, bool TRACE>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int D = NXV * 128;
@@ -669,7 +803,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     // partial-sum gather (never live together)
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + off);
     float* att_sc = reinterpret_cast<float*>(smem_raw + off);            // [160]
-    float* att_op = reinterpret_cast<float*>(smem_raw + off + 1024);     // [256]
+    float* att_op = reinterpret_cast<float*>(smem_raw + off + 1024);     // [1024]
     float* part = reinterpret_cast<float*>(smem_raw + off);              // [2][D]
     float* gat = reinterpret_cast<float*>(smem_raw + off);               // [G][8]
     off += MEGA_SCRATCH_BYTES;
@@ -694,6 +828,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     int* iscr = reinterpret_cast<int*>(smem_raw + off);
     off += 16 * sizeof(int);
     volatile int* ctl = reinterpret_cast<volatile int*>(smem_raw + off);  // [0] stop flag, [1] tiles consumed, [2] token
+    ring.landed = reinterpret_cast<uint32_t*>(smem_raw + off) + 3;        // [3] tiles the producer has seen landed
     off += 4 * sizeof(int);
     unsigned char* seen = smem_raw + off;  // [Vpad]
 
@@ -705,6 +840,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
         ctl[0] = 0;
         ctl[1] = 0;
         ctl[2] = 0;
+        ctl[3] = 0;
         mbar_fence_init();
     }
     for (int i = tid_all; i < p.Vpad; i += MEGA_THREADS) seen[i] = p.seen[i];
@@ -722,6 +858,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
         // ================= producer warp =================
         if (tid_all == MEGA_CONSUMERS) {
             Producer pr(ring, ctl, (uint32_t)max(1, min(p.window, NSLOT)));
+            pr.region = p.stream + cta_base(sd, cta);
+            pr.region_floats = cta_base(sd, cta + 1) - cta_base(sd, cta);
+            pr.ahead_floats = min((long long)p.l2_ahead_tiles * slot_floats(D), pr.region_floats - slot_floats(D));
+            if (pr.ahead_floats < 0) pr.ahead_floats = 0;
             bool ok = true;
             for (int i = 0; i < p.n_steps && ok; ++i) {
                 if (i == 0 && had_pending) continue;
@@ -732,6 +872,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
             // the full-barrier of every tile that was issued but never consumed.
             uint32_t spins = 0;
             while (!ctl[0]) {
+                pr.advance();
                 if (++spins > (1u << 30)) __trap();
                 __nanosleep(64);
             }
@@ -771,16 +912,21 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     float shift1 = 0.0f, shift2 = 0.0f;  // statistics shifts of ln_1 / ln_2: the means seen one layer earlier
 
     for (int i = 0; i < p.n_steps; ++i) {
-        const bool tr = p.trace != nullptr && i == p.trace_step && tid == 0;
-        unsigned long long* trow = p.trace + (size_t)cta * p.trace_slots;
+        // debug timeline (compiled out of the production instantiation)
+        const bool tr = TRACE && p.trace != nullptr && i == p.trace_step && tid == 0;
+        unsigned long long* trow = TRACE ? p.trace + (size_t)cta * p.trace_slots : nullptr;
         auto stamp = [&](int slot) {
-            if (tr && slot < p.trace_slots) trow[slot] = globaltimer_ns();
+            if constexpr (TRACE) {
+                if (tr && slot < p.trace_slots) trow[slot] = globaltimer_ns();
+            }
         };
         stamp(p.L * GV_TRACE_PER_LAYER + 4);
-        cs.wacc = tr ? &wait_ns : nullptr;
+        if constexpr (TRACE) cs.wacc = tr ? &wait_ns : nullptr;
         auto stamp_wait = [&](int slot) {  // stores the weight-wait time accumulated since the previous call
-            if (tr && slot < p.trace_slots) trow[slot] = wait_ns;
-            wait_ns = 0;
+            if constexpr (TRACE) {
+                if (tr && slot < p.trace_slots) trow[slot] = wait_ns;
+                wait_ns = 0;
+            }
         };
         float4 lat = make_float4(0.f, 0.f, 0.f, 0.f);  // final_norm(ln_f(x)): the latent of this step (elements 4 tid ..)
         if (!(i == 0 && had_pending)) {
@@ -834,7 +980,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
 #define GV_ATT_CASE(hd)                                                                                                     \
     case hd:                                                                                                                \
         att_item<hd>(kh, vh, p.xq, D, h, j0, j1, S, tg + TG_XQ, hc + HC_XQ * GV_HOP_STRIDE, t_xq, att_sc, att_op, tid,      \
-                     p.att_o, p.att_ml, cta, tg + TG_AO, tmask);                                                            \
+                     p.att_o, p.att_ml, cta, tg + TG_AO, tmask, (TRACE && tr && ts + 20 <= p.trace_slots) ? trow + ts + 14 : nullptr); \
         break;
                     switch (HD) {
                         GV_ATT_CASE(32) GV_ATT_CASE(64) GV_ATT_CASE(128) GV_ATT_CASE(256)
@@ -1081,13 +1227,18 @@ size_t mega_smem_bytes(int D, int Vpad) {
     return (off + 15) & ~size_t(15);
 }
 
-template <int NXV>
-static cudaError_t launch_nxv(const MegaParams& p, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<NXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int NXV, bool TRACE>
+static cudaError_t launch_nxv2(const MegaParams& p, int grid, size_t smem, cudaStream_t st) {
+    cudaError_t e =
+        cudaFuncSetAttribute(decode_mega_kernel<NXV, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     MegaParams pp = p;
     void* args[] = {&pp};
-    return cudaLaunchCooperativeKernel((void*)decode_mega_kernel<NXV>, dim3(grid), dim3(MEGA_THREADS), args, smem, st);
+    return cudaLaunchCooperativeKernel((void*)decode_mega_kernel<NXV, TRACE>, dim3(grid), dim3(MEGA_THREADS), args, smem, st);
+}
+template <int NXV>
+static cudaError_t launch_nxv(const MegaParams& p, int grid, size_t smem, cudaStream_t st) {
+    return p.trace != nullptr ? launch_nxv2<NXV, true>(p, grid, smem, st) : launch_nxv2<NXV, false>(p, grid, smem, st);
 }
 
 cudaError_t launch_decode_mega(const MegaParams& p, int grid, cudaStream_t st) {

@@ -14,7 +14,7 @@ enum { HC_XQ = 0, HC_AO = 1, HC_X1 = 2, HC_PP = 3, HC_X2 = 4, HC_LG = 5, HC_COUN
 // exchange tags of one forward: tag(layer l, buffer b) = tbase + GV_TAGS_PER_LAYER*l + b; logits = tbase + GV_TAGS_PER_LAYER*L
 #define GV_TAGS_PER_LAYER 5
 // debug timeline slots per layer (genvc_debug_trace)
-#define GV_TRACE_PER_LAYER 14
+#define GV_TRACE_PER_LAYER 20
 
 struct MegaParams {
     int L, D, H, V, Vpad, S_max;
@@ -58,6 +58,7 @@ struct MegaParams {
     int trace_step, trace_slots;
     // tuning / debug knobs (genvc_debug_tune)
     int window;      // producer: max tiles in flight (1..GV_MEGA_NSLOT)
+    int l2_ahead_tiles;  // producer: L2 prefetch distance in tiles (0 = off)
     int dbg_nosync;  // consumers do not wait for exchange data (results are garbage; streaming-rate probe)
 };
 

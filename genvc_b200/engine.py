@@ -265,15 +265,16 @@ class Engine:
             self._check(self.lib.genvc_debug_trace(self._ctx, None, 0, 0))
             self._trace = None
             return None
-        slots = self.dims.n_layer * 14 + 8
+        slots = self.dims.n_layer * 20 + 8
         g = self.decode_grid
         self._trace = torch.zeros(g * slots, dtype=torch.int64, device=self.device)
         self._check(self.lib.genvc_debug_trace(self._ctx, self._trace.data_ptr(), slots, int(step)))
         return self._trace.view(g, slots)
 
-    def tune(self, window: int = 0, nosync: bool = False):
-        """Fused-kernel knobs: TMA tiles in flight per SM; ``nosync`` = streaming-rate probe (garbage results)."""
-        self._check(self.lib.genvc_debug_tune(self._ctx, int(window), int(bool(nosync))))
+    def tune(self, window: int = 0, nosync: bool = False, l2_ahead: int = -1):
+        """Fused-kernel knobs: TMA tiles in flight per SM; ``nosync`` = streaming-rate probe (garbage results);
+        ``l2_ahead`` = HBM->L2 prefetch distance in tiles (-1 keeps the current value)."""
+        self._check(self.lib.genvc_debug_tune(self._ctx, int(window), int(bool(nosync)), int(l2_ahead)))
 
     # ------------------------------------------------------------------ microbenchmark
     def kv_attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S: int) -> torch.Tensor:

@@ -181,8 +181,10 @@ int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, in
 /* Tuning / debug knobs of the fused decode kernel (no reference counterpart):
  *   window > 0 : weight tiles the per-SM TMA producer keeps in flight (requested, not landed);
  *   nosync != 0: consumers do not wait for exchange data — results are garbage; probes the pure
- *                weight-streaming rate.  Never set outside profiling. */
-int genvc_debug_tune(genvc_ctx* ctx, int window, int nosync);
+ *                weight-streaming rate.  Never set outside profiling;
+ *   l2_ahead_tiles >= 0: distance (in 16 KB tiles per SM) at which the producer prefetches the
+ *                weight stream HBM -> L2 ahead of the shared-memory ring (0 = off; < 0 keeps). */
+int genvc_debug_tune(genvc_ctx* ctx, int window, int nosync, int l2_ahead_tiles);
 
 #ifdef __cplusplus
 }

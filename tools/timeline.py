@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 # trace slots per layer (include/genvc_b200.h)
-TPL = 14
+TPL = 20
 SEGMENTS = [
     ("x2 hop + load", None, 0), ("LN1", 0, 1), ("QKV gemv", 1, 2), ("attention item", 2, 3), ("AO hop + merge", 3, 4),
     ("PROJ gemv", 4, 5), ("x1 hop + load", 5, 6), ("LN2", 6, 7), ("FC gemv", 7, 8), ("P2 gemv", 8, 9), ("PP hop", 9, 10),
@@ -64,6 +64,9 @@ def analyse(tr: torch.Tensor, L: int) -> dict:
         "logits hop + load": float((tr[:, head + 2] - tr[:, head + 1]).median()),
         "sample": float((tr[:, head + 3] - tr[:, head + 2]).median()),
     }
+    att = ww[:, 1:, 14:20]
+    sel = att[:, :, 0] > 0
+    out["att_cycles"] = [float(att[:, :, k][sel].median()) if sel.any() else 0.0 for k in range(6)]
     out["layer_ns"] = float((tr[:, (L - 1) * TPL].max() - tr[:, 0].max()) / max(L - 1, 1)) if L > 1 else 0.0
     out["step_ns"] = float(tr[:, head + 3].max() - t0)
     return out
@@ -78,6 +81,7 @@ def main():
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--window", type=int, nargs="*", default=[0])
     ap.add_argument("--nosync", type=int, default=0)
+    ap.add_argument("--ahead", type=int, nargs="*", default=[-1])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline.json"))
     args = ap.parse_args()
     from genvc_b200.config import GenVCDims
@@ -96,8 +100,8 @@ def main():
     kw = dict(do_sample=True, top_p=0.85, top_k=1, temperature=0.85, repetition_penalty=2.0, ignore_eos=True,
               max_new_tokens=24, stream_chunk_size=8, decode_mode=args.mode)
     res = {}
-    for win in args.window:
-        eng.tune(window=win, nosync=bool(args.nosync))
+    for win, ahead in [(w, a) for w in args.window for a in args.ahead]:
+        eng.tune(window=win, nosync=bool(args.nosync), l2_ahead=ahead)
         for rep in range(3):  # warm-up, then two traced runs (steps 2 and 6 of the 2nd launch)
             tr = eng.trace(step=(2 if rep < 2 else 6))
             fake = g.compute_embeddings(cond, codes)
@@ -108,8 +112,8 @@ def main():
             t1.record()
             torch.cuda.synchronize()
             if rep > 0:
-                res[f"win{win}_run{rep}"] = analyse(tr, args.layers)
-                res[f"win{win}_run{rep}"]["segment_ms"] = t0.elapsed_time(t1)
+                res[f"win{win}_ahead{ahead}_run{rep}"] = analyse(tr, args.layers)
+                res[f"win{win}_ahead{ahead}_run{rep}"]["segment_ms"] = t0.elapsed_time(t1)
     eng.trace(None)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
@@ -119,7 +123,8 @@ def main():
         for name, a in v["segments"].items():
             print(f"  {name:20s} med {a['med']/1e3:6.2f} us  max {a['max']/1e3:6.2f}  critical-path {a['crit']/1e3:6.2f}")
         print("  head:", {n: round(x / 1e3, 2) for n, x in v["head"].items()})
-        print("  weight wait per layer (thread 0):", {n: round(x / 1e3, 2) for n, x in v["weight_wait_ns"].items()})
+        print("  attention item cycles (prefetch issue, XQ hop wait, tagged loads, scores+barrier, softmax, PV+merge):", [int(x) for x in v["att_cycles"]])
+        print("  weight wait per layer (thread 0):", {n: int(x) for n, x in v["weight_wait_ns"].items()}, "cycles")
 
 
 if __name__ == "__main__":
