@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/genvc_b200.h"
 #include "layout.h"
@@ -197,7 +198,10 @@ int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
     return GENVC_OK;
 }
 
-void genvc_destroy(genvc_ctx* ctx) { delete ctx; }
+void genvc_destroy(genvc_ctx* ctx) {
+    if (ctx && ctx->blob) gemm_tc_forget(ctx->blob, ctx->blob + ctx->layout.total);
+    delete ctx;
+}
 
 const char* genvc_last_error(const genvc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
@@ -227,10 +231,61 @@ int genvc_tensor_info(const genvc_ctx* ctx, const char* key, uint64_t* offset, u
     return GENVC_OK;
 }
 
+// the dense matrices the batched (prefill / latent pass / perceiver) GEMMs stream: {offset, N, K, ldw, w_nk}
+struct TcMat {
+    uint64_t off;
+    int N, K, ldw, w_nk;
+};
+static std::vector<TcMat> tc_matrices(const genvc_ctx* c) {
+    const genvc_config& g = c->cfg;
+    const int D = g.d_model, inner = g.pc_dim_head * g.pc_heads, ffi = g.pc_ff_inner;
+    std::vector<TcMat> v;
+    for (const LayerOff& o : c->layout.layers) {
+        v.push_back({o.attn_w, 3 * D, D, 3 * D, 0});
+        v.push_back({o.proj_w, D, D, D, 0});
+        v.push_back({o.fc_w, 4 * D, D, 4 * D, 0});
+        v.push_back({o.proj2_w, D, 4 * D, D, 0});
+    }
+    for (const PcLayerOff& o : c->layout.pc_layers) {
+        v.push_back({o.to_q, inner, D, D, 1});
+        v.push_back({o.to_kv, 2 * inner, D, D, 1});
+        v.push_back({o.to_out, D, inner, inner, 1});
+        v.push_back({o.ff0_w, 2 * ffi, D, D, 1});
+    }
+    std::vector<TcMat> ok;
+    for (const TcMat& m : v)
+        if (gemm_tc_packed_floats(m.N, m.K) > 0) ok.push_back(m);
+    return ok;
+}
+
+uint64_t genvc_tc_floats(const genvc_ctx* ctx) {
+    if (!ctx) return 0;
+    uint64_t t = 0;
+    for (const TcMat& m : tc_matrices(ctx)) t += gemm_tc_packed_floats(m.N, m.K);
+    return t;
+}
+
+int genvc_pack_tc(genvc_ctx* ctx, float* tc_dev, uint64_t n_floats, void* stream) {
+    if (!ctx) return GENVC_E_INVALID;
+    if (!ctx->blob) return ctx->fail(GENVC_E_STATE, "bind weights first");
+    if (!tc_dev || n_floats < genvc_tc_floats(ctx) || reinterpret_cast<uintptr_t>(tc_dev) % 128)
+        return ctx->fail(GENVC_E_INVALID, "tensor-core weight buffer too small or misaligned");
+    CK(cudaSetDevice(ctx->device));
+    uint64_t o = 0;
+    for (const TcMat& m : tc_matrices(ctx)) {
+        CK(gemm_tc_pack(ctx->w(m.off), m.N, m.K, m.ldw, m.w_nk, tc_dev + o, (cudaStream_t)stream));
+        ctx->nlaunch += 1;
+        o += gemm_tc_packed_floats(m.N, m.K);
+    }
+    return GENVC_OK;
+}
+
 int genvc_bind_weights(genvc_ctx* ctx, const float* blob_dev, uint64_t n_floats) {
     if (!ctx) return GENVC_E_INVALID;
     if (!blob_dev || n_floats < ctx->layout.total) return ctx->fail(GENVC_E_INVALID, "weight blob too small");
     if (reinterpret_cast<uintptr_t>(blob_dev) % 128) return ctx->fail(GENVC_E_INVALID, "weight blob must be 128-byte aligned");
+    if (ctx->blob) gemm_tc_forget(ctx->blob, ctx->blob + ctx->layout.total);
+    gemm_tc_forget(blob_dev, blob_dev + ctx->layout.total);
     ctx->blob = blob_dev;
     ctx->stream_packed = false;
     return GENVC_OK;

@@ -3,6 +3,8 @@
 // rules TF32/bf16 out for this path.
 #include "attn_decode.cuh"
 #include "common.cuh"
+#include <cstdlib>
+
 #include "ops.cuh"
 #include "sampling.cuh"
 
@@ -154,10 +156,34 @@ __global__ void splitk_epilogue_kernel(GemmArgs a, const float* __restrict__ ws,
     }
 }
 
+// GENVC_TC=0 in the environment keeps every GEMM on the fp32 CUDA-core kernel (debug / A-B comparison)
+static bool use_tensor_cores() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GENVC_TC");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 cudaError_t launch_gemm(const GemmArgs& a, float* ws, size_t ws_floats, const int* skip, cudaStream_t st,
                         unsigned long long* nlaunch) {
     if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaErrorInvalidValue;
     if ((a.K & 3) || (a.lda & 3) || (a.ldw & 3)) return cudaErrorInvalidValue;
+    if (use_tensor_cores() && gemm_tc_eligible(a)) {
+        // dense contraction with enough rows: tcgen05 3xTF32 kernel (gemm_tc.cu)
+        int splits = 1;
+        cudaError_t e = launch_gemm_tc(a, ws, ws_floats, skip, st, &splits);
+        if (e != cudaSuccess) return e;
+        GV_BUMP(nlaunch);
+        if (splits > 1) {
+            size_t total = (size_t)a.M * a.N;
+            int blocks = (int)min((size_t)1184, (total + 255) / 256);
+            splitk_epilogue_kernel<<<blocks, 256, 0, st>>>(a, ws, splits, skip);
+            GV_BUMP(nlaunch);
+        }
+        return cudaGetLastError();
+    }
     const int BM = a.M <= 16 ? 16 : (a.M <= 32 ? 32 : 64);
     dim3 grid((a.N + 63) / 64, (a.M + BM - 1) / BM, 1);
     // deterministic split-K when the tile grid cannot fill the machine

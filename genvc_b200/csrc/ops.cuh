@@ -71,6 +71,15 @@ struct SampleArgs {
     int step_in_call;
 };
 
+// tcgen05 3xTF32 GEMM (gemm_tc.cu).  Weights are pre-split / pre-tiled once (gemm_tc_pack registers the tiled copy
+// under the reference-layout pointer W); launch_gemm routes a GEMM whose W is registered to the tensor-core
+// kernel (it reports the split-K factor it used; the caller runs the split-K reduction epilogue when > 1).
+size_t gemm_tc_packed_floats(int N, int K);  // 0 when K is not a multiple of 32 (not eligible)
+cudaError_t gemm_tc_pack(const float* W, int N, int K, int ldw, int w_nk, float* out, cudaStream_t st);
+void gemm_tc_forget(const float* lo, const float* hi);  // drop registrations of weights inside [lo, hi)
+bool gemm_tc_eligible(const GemmArgs& a);
+cudaError_t launch_gemm_tc(const GemmArgs& a, float* splitk_ws, size_t splitk_ws_floats, const int* skip, cudaStream_t st,
+                           int* splits_out);
 cudaError_t launch_gemm(const GemmArgs& a, float* splitk_ws, size_t splitk_ws_floats, const int* skip,
                         cudaStream_t st, unsigned long long* nlaunch);
 // rows are addressed as group g = r / rpg, i = r % rpg: X + g * x_gs + i * x_stride

@@ -9,6 +9,7 @@ returns immediately; nothing here synchronises except where a result is read on 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -87,6 +88,8 @@ class Engine:
             raise GenvcError(rc, msg)
         self.blob: Optional[torch.Tensor] = None
         self.wstream: Optional[torch.Tensor] = None
+        self.wtc: Optional[torch.Tensor] = None
+        self.use_tensor_cores = os.environ.get("GENVC_TC", "1") != "0"
         with torch.cuda.device(self.device):
             self.kv = torch.zeros(int(self.lib.genvc_kv_floats(self._ctx)), dtype=torch.float32, device=self.device)
             self.ws = torch.zeros(int(self.lib.genvc_workspace_bytes(self._ctx)), dtype=torch.uint8, device=self.device)
@@ -166,6 +169,11 @@ class Engine:
             if n > 0:
                 self.wstream = torch.empty(n, dtype=torch.float32, device=self.device)
                 self._check(self.lib.genvc_pack_stream(self._ctx, self.wstream.data_ptr(), n, self._stream()))
+            # TF32 hi|lo pre-tiled copy of the dense matrices for the tcgen05 GEMMs (prefill / latent pass / perceiver)
+            n = int(self.lib.genvc_tc_floats(self._ctx))
+            if n > 0 and self.use_tensor_cores:
+                self.wtc = torch.empty(n, dtype=torch.float32, device=self.device)
+                self._check(self.lib.genvc_pack_tc(self._ctx, self.wtc.data_ptr(), n, self._stream()))
 
     # ------------------------------------------------------------------ the path
     def perceiver(self, mel: torch.Tensor) -> torch.Tensor:

@@ -56,6 +56,8 @@ SIGNATURES = {
     "genvc_bind_weights": (C.c_int, [_P, _P, C.c_uint64]),
     "genvc_stream_floats": (C.c_uint64, [_P]),
     "genvc_pack_stream": (C.c_int, [_P, _P, C.c_uint64, _P]),
+    "genvc_tc_floats": (C.c_uint64, [_P]),
+    "genvc_pack_tc": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "genvc_kv_floats": (C.c_uint64, [_P]),
     "genvc_workspace_bytes": (C.c_uint64, [_P]),
     "genvc_bind_buffers": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64]),

@@ -105,6 +105,13 @@ int genvc_bind_weights(genvc_ctx* ctx, const float* blob_dev, uint64_t n_floats)
 uint64_t genvc_stream_floats(const genvc_ctx* ctx);
 int genvc_pack_stream(genvc_ctx* ctx, float* stream_dev, uint64_t n_floats, void* stream);
 
+/* Tensor-core weight copy: the dense matrices of the batched GEMMs (prefill, latent pass, perceiver projections)
+ * pre-split into TF32 hi | lo halves and pre-tiled into 32 KB blocks (128 output columns x 32 k in the UMMA
+ * canonical layout) so that one bulk TMA copy feeds one tcgen05 pipeline stage.  Optional: without it those GEMMs
+ * run on the fp32 CUDA-core kernel.  The buffer must stay valid while the weights are bound. */
+uint64_t genvc_tc_floats(const genvc_ctx* ctx);
+int genvc_pack_tc(genvc_ctx* ctx, float* tc_dev, uint64_t n_floats, void* stream);
+
 /* ---- caller-owned scratch -------------------------------------------------- */
 uint64_t genvc_kv_floats(const genvc_ctx* ctx);       /* [L][2][max_batch][H][max_seq][hd] */
 uint64_t genvc_workspace_bytes(const genvc_ctx* ctx);
