@@ -56,7 +56,8 @@ struct genvc_ctx {
     // workspace offsets (bytes)
     size_t o_state, o_seen, o_status_scratch, o_pend_logits, o_pend_latent, o_splitk, o_X, o_A, o_QKV, o_U;
     // exchange buffers of the fused decode kernel ({value, tag} pairs; one contiguous region)
-    size_t o_xchg, xchg_bytes, o_xq, o_matt_o, o_matt_ml, o_x1, o_pp, o_x2, o_lg, o_hops;
+    size_t o_xchg, xchg_bytes, o_xq, o_matt_o, o_matt_ml, o_x1, o_pp, o_x2, o_lg, o_hops, o_acc;
+    size_t acc_bytes = 0;
     uint32_t tag_next = 1;
     size_t o_pc_melT, o_pc_ctx, o_pc_kv, o_pc_lat, o_pc_q, o_pc_o, o_pc_h, o_pc_g;
     size_t ws_bytes = 0;
@@ -127,6 +128,8 @@ static void plan_workspace(genvc_ctx* c) {
     c->o_x2 = w.take(2 * D * F);
     c->o_lg = w.take(2 * (size_t)c->Vpad * F);
     c->o_hops = w.take(HC_COUNT * GV_HOP_STRIDE * sizeof(unsigned));
+    c->acc_bytes = 2 * (size_t)g.n_layer * D * sizeof(unsigned long long);
+    c->o_acc = w.take(c->acc_bytes);
     c->xchg_bytes = w.take(0) - c->o_xchg;
     c->o_splitk = w.take(kSplitKFloats * F);
     const size_t R = c->rows_cap();
@@ -595,6 +598,8 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         p.lg = ctx->at<float>(ctx->o_lg);
         p.hops = ctx->at<unsigned>(ctx->o_hops);
         CK(cudaMemsetAsync(p.hops, 0, HC_COUNT * GV_HOP_STRIDE * sizeof(unsigned), st));
+        p.acc = ctx->at<unsigned long long>(ctx->o_acc);
+        CK(cudaMemsetAsync(p.acc, 0, ctx->acc_bytes, st));
         {   // exchange tags: unique per (launch, step, layer, buffer); restart over zeroed buffers before a wrap
             const uint64_t need = (uint64_t)n_steps * ((uint64_t)GV_TAGS_PER_LAYER * g.n_layer + 1ull);
             if ((uint64_t)ctx->tag_next + need >= 0xFFFFFFF0ull) {

@@ -32,7 +32,8 @@ struct MegaParams {
     float* att_o;   // [items][hd] un-normalised partial attention outputs
     float* att_ml;  // [items][2]  (max, sum)
     float* x1;      // [D]  residual stream after attention
-    float* pp;      // [G][D] per-CTA partial sums of mlp.c_proj
+    float* pp;      // [G][D] per-CTA partial sums of mlp.c_proj (reducer-CTA variant)
+    unsigned long long* acc;  // [2][L][D] self-counting fixed-point accumulators of mlp.c_proj (zero at launch)
     float* x2;      // [D]  residual stream leaving the block
     float* lg;      // [V]  logits
     unsigned* hops;  // [HC_COUNT * GV_HOP_STRIDE] arrival counters, zero at launch

@@ -224,3 +224,25 @@ def test_philox_sampling_is_seed_reproducible(cuda_device):
     assert torch.equal(a, b)
     assert not torch.equal(a, c)
     assert (a >= 0).all() and (a < 1026).all()
+
+
+# ------------------------------------------------------------------------------------ KV-cache attention microbenchmark
+@pytest.mark.parametrize("H,hd", [(4, 256), (16, 64), (4, 32), (2, 128)])
+@pytest.mark.parametrize("S", [1, 7, 64, 333])
+def test_kv_attention_matches_torch(H, hd, S, cuda_device):
+    """genvc_kv_attention (BASELINE configs[4]) against a plain fp32 torch evaluation of HF GPT2Attention._attn for one
+    query: softmax(q k^T / sqrt(hd)) v.  Tolerance: two fp32 summation orders (online softmax vs torch): 2e-5 abs."""
+    from genvc_b200.config import GenVCDims, make_config_dict
+    from genvc_b200.engine import Engine
+
+    eng = Engine(GenVCDims.from_config(make_config_dict(2, 128, 4)), cuda_device)
+    g = torch.Generator().manual_seed(S * 131 + hd)
+    N, S_max = 5, S + 3
+    k = torch.randn((N, H, S_max, hd), generator=g).to(cuda_device)
+    v = torch.randn((N, H, S_max, hd), generator=g).to(cuda_device)
+    q = torch.randn((N, H, hd), generator=g).to(cuda_device)
+    out = eng.kv_attention(q, k, v, S)
+    p = torch.softmax(torch.einsum("nhd,nhsd->nhs", q, k[:, :, :S]) / hd ** 0.5, -1)
+    ref = torch.einsum("nhs,nhsd->nhd", p, v[:, :, :S])
+    ok, err = close(out, ref, 2e-5, 1e-4)
+    assert ok, f"kv attention max err {err}"
