@@ -231,6 +231,9 @@ __device__ __forceinline__ void ld_tagged_vec(const float* buf, int idx, uint32_
 // contributors, so a reader knows from the word itself when all G (< 256) CTAs have arrived — no fence, no
 // separate reducer CTAs, one hop instead of three.
 // ---------------------------------------------------------------------------------------------
+#ifndef GV_PP_COUNTER
+#define GV_PP_COUNTER 1  /* 0 = reducer CTAs poll the partial-sum tags directly: measured slower (0.643 vs 0.631 ms/token) */
+#endif
 #ifndef GV_ATOMIC_RED
 #define GV_ATOMIC_RED 0  /* measured on B200: 148 x 1024 u64 reductions onto 8 KB cost ~6 us per layer (L2 serialises per line); the reducer-CTA path below is faster */
 #endif
@@ -527,13 +530,13 @@ __device__ __forceinline__ void st_vec(float* p, const float* r) {
     else __stcg(p, r[0]);
 }
 
-template <int HD>
+template <int HD, bool DBG>
 __device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict__ Vc, const float* xq, int D, int h, int j0, int j1, int S,
                          uint32_t tag_in, const unsigned* cnt_in, unsigned target_in, float* sc, float* opart, int tid,
                          float* o_out, float* ml_out, int item, uint32_t tag_out, uint32_t tmask, unsigned long long* dbg) {
     using L = AttLane<HD>;
     long long ck[8];
-    ck[0] = clock64();
+    if constexpr (DBG) ck[0] = clock64();
     constexpr int VEC = L::VEC, NCH = L::NCH, DPL = L::DPL;
     constexpr int DV = HD / 4;               // PV stage: a thread owns 4 consecutive dims, DV threads cover a key
     constexpr int NS = MEGA_CONSUMERS / DV;  // key slices of the PV stage
@@ -564,12 +567,12 @@ __device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict_
     for (int u = 0; u < ATT_ROWS; ++u) load_k_row(warp + MEGA_WARPS * u, kr[u]);
 #pragma unroll
     for (int i = 0; i < VPRE; ++i) vr[i] = load_v(ks + NS * i);
-    ck[1] = clock64();
+    if constexpr (DBG) ck[1] = clock64();
     // no counter wait here: only the <= H * 8 attention CTAs read xq, so they poll the tagged words directly (one L2
     // round trip less than counter-then-data; the all-CTA hops keep the counter because 148 x 256 pollers contend)
     (void)cnt_in;
     (void)target_in;
-    ck[2] = clock64();
+    if constexpr (DBG) ck[2] = clock64();
     // ---- this step's q, and k / v of the position being decoded: every tagged load in flight at once ----
     float qr[DPL], knew[DPL];
     float4 vnew = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -623,7 +626,7 @@ __device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict_
             if (++spins > MEGA_SPIN_LIMIT) __trap();
         }
     }
-    ck[3] = clock64() + (long long)(qr[0] == 123.f);
+    if constexpr (DBG) ck[3] = clock64() + (long long)(qr[0] == 123.f);
     if (v_mine) __stcg(reinterpret_cast<float4*>(Vc + (size_t)(S - 1) * HD + d), vnew);
     if (k_mine) {
 #pragma unroll
@@ -661,7 +664,7 @@ __device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict_
         }
     }
     bar_sync(1, MEGA_CONSUMERS);
-    ck[4] = clock64();
+    if constexpr (DBG) ck[4] = clock64();
     // ---- softmax weights (every warp, all keys) ----
     float pv[ATT_MAX_BLOCKS];
     float M = -INFINITY;
@@ -685,7 +688,7 @@ __device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict_
         }
     }
     Lsum = warp_sum(Lsum);
-    ck[5] = clock64() + (long long)(Lsum == 123.f);
+    if constexpr (DBG) ck[5] = clock64() + (long long)(Lsum == 123.f);
     // ---- PV ----
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -714,14 +717,16 @@ __device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict_
 #pragma unroll
         for (int q = 0; q < NS; ++q) os += opart[q * HD + tid];
     }
-    ck[6] = clock64() + (long long)(os == 123.f);
+    if constexpr (DBG) ck[6] = clock64() + (long long)(os == 123.f);
     if (tid < HD) {
         st_tagged(o_out, item * HD + tid, os, tag_out);
         if (tid == 0) st_tagged2(ml_out, item * 2, M, Lsum, tag_out);
     }
-    if (dbg != nullptr && tid == 0) {
+    if constexpr (DBG) {
+      if (dbg != nullptr && tid == 0) {
 #pragma unroll
         for (int q = 0; q < 6; ++q) dbg[q] = (unsigned long long)(ck[q + 1] - ck[q]);
+      }
     }
 }
 
@@ -938,7 +943,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     const float* mel_emb = p.blob + p.mel_emb_off;
     const float* mel_pos = p.blob + p.mel_pos_off;
     unsigned* const hc = p.hops;
-    unsigned t_xq = 0, t_ao = 0, t_x1 = 0, t_pp = 0, t_x2 = 0, t_lg = 0;  // hop counter targets (counters are zero at launch)
+    // hop counter targets (counters are zero at launch): x1 / pp / x2 advance by a fixed amount per layer, so they are
+    // derived from one layer counter; only the attention target (items vary with S) and the logits target are running sums
+    unsigned lc = 0, t_ao = 0, t_lg = 0;
     float shift1 = 0.0f, shift2 = 0.0f;  // statistics shifts of ln_1 / ln_2: the means seen one layer earlier
 
     for (int i = 0; i < p.n_steps; ++i) {
@@ -993,7 +1000,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     }
 #else
                     } else {
-                        hop_wait(hc + HC_X2 * GV_HOP_STRIDE, t_x2, tid, tmask);
+                        hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask);
                         if (xvalid) ld_tagged_vec<4>(p.x2, 4 * tid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask, &x.x);
                     }
 #endif
@@ -1010,7 +1017,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     });
                     cs.gt += (uint32_t)ntl[PH_QKV];
                     stamp(ts + 2);
-                    t_xq += (unsigned)G;  // (xq needs no arrival counter: its readers poll the tags)
                 }
                 // ---- ATT: (head, key-range) items on the first n_items CTAs ----
                 if (cta < n_items) {
@@ -1020,7 +1026,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     float* vh = vc + (size_t)h * p.S_max * HD;
 #define GV_ATT_CASE(hd)                                                                                                     \
     case hd:                                                                                                                \
-        att_item<hd>(kh, vh, p.xq, D, h, j0, j1, S, tg + TG_XQ, hc + HC_XQ * GV_HOP_STRIDE, t_xq, att_sc, att_op, tid,      \
+        att_item<hd, TRACE>(kh, vh, p.xq, D, h, j0, j1, S, tg + TG_XQ, hc + HC_XQ * GV_HOP_STRIDE, 0u, att_sc, att_op, tid,      \
                      p.att_o, p.att_ml, cta, tg + TG_AO, tmask, (TRACE && tr && ts + 20 <= p.trace_slots) ? trow + ts + 14 : nullptr); \
         break;
                     switch (HD) {
@@ -1086,11 +1092,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     stamp(ts + 5);
                     stamp_wait(ts + 12);
                     hop_arrive(hc + HC_X1 * GV_HOP_STRIDE, tid);
-                    t_x1 += (unsigned)G;
                 }
                 // ---- FC + P2: u = gelu_new(LN2(x1) . W_fc + b) (kept in this CTA) -> partial of u . W_proj2 ----
                 {
-                    hop_wait(hc + HC_X1 * GV_HOP_STRIDE, t_x1, tid, tmask);
+                    hop_wait(hc + HC_X1 * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask);
                     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (xvalid) {
                         ld_tagged_vec<4>(p.x1, 4 * tid, tg + TG_X1, tmask, &x.x);
@@ -1127,9 +1132,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     stamp(ts + 9);
                     stamp_wait(ts + 13);
                     hop_arrive(hc + HC_PP * GV_HOP_STRIDE, tid);
-                    t_pp += (unsigned)G;
                     // x2 = x1 + b + sum of the G partials: every CTA reads the finished accumulators itself
-                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, t_pp, tid, tmask);
+                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask);
                     if (xvalid) {
                         const unsigned long long full_count = (unsigned long long)(G & 0xff);
                         ulonglong2 w0 = ld_x2u64(accl), w1 = ld_x2u64(accl + 2);
@@ -1146,6 +1150,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     }
                     stamp(ts + 11);
                 }
+                lc += 1u;
 #else
                     if (xvalid) {
                         const float4 p0 = *reinterpret_cast<const float4*>(part + 4 * tid);
@@ -1155,14 +1160,19 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     }
                     stamp(ts + 9);
                     stamp_wait(ts + 13);
+#if GV_PP_COUNTER
                     hop_arrive(hc + HC_PP * GV_HOP_STRIDE, tid);
-                    t_pp += (unsigned)G;
+#else
+                    bar_sync(1, MEGA_CONSUMERS);  // `part` / `gat` alias: all reads of `part` precede the gather below
+#endif
                 }
                 // ---- RED: x2 = x1 + b + sum over CTAs of the partials (8 outputs per reducer CTA) ----
                 if (cta < n_red) {
                     float b2 = 0.0f;
                     if (lane == 0) b2 = __ldg(p.blob + p.proj2_b_off + (long long)l * p.layer_stride + cta * 8 + warp);
-                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, t_pp, tid, tmask);
+#if GV_PP_COUNTER
+                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask);
+#endif
                     stamp(ts + 10);
                     {   // load q: 16 bytes {v, tag, v, tag} of source CTA q / 4, outputs 2 (q % 4), +1; three rounds in flight
                         const uint32_t tgp = tg + TG_PP;
@@ -1204,7 +1214,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     stamp(ts + 11);
                     hop_arrive(hc + HC_X2 * GV_HOP_STRIDE, tid);
                 }
-                t_x2 += (unsigned)n_red;
+                lc += 1u;
 #endif
             }
             // ---- HEAD: ln_f -> final_norm -> latent z ; logits = z . mel_head^T + b ----
@@ -1214,7 +1224,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
 #if GV_ATOMIC_RED
                 lat = xnext;
 #else
-                hop_wait(hc + HC_X2 * GV_HOP_STRIDE, t_x2, tid, tmask);
+                hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask);
                 if (xvalid) ld_tagged_vec<4>(p.x2, 4 * tid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask, &lat.x);
 #endif
                 stamp(ts + 0);
