@@ -66,7 +66,7 @@ struct genvc_ctx {
     // debug timeline of the fused decode kernel (genvc_debug_trace)
     unsigned long long* trace = nullptr;
     int trace_slots = 0, trace_step = 0;
-    int window = 4, dbg_nosync = 0, l2_ahead = 0;
+    int window = 3, dbg_nosync = 0, l2_ahead = 0, hop_settle = 0, hop_hold = 0;
 
     // host mirror of the generation state
     int B = 0, P = 0;
@@ -349,10 +349,12 @@ int genvc_bind_buffers(genvc_ctx* ctx, float* kv_dev, uint64_t kv_floats, void* 
 
 uint64_t genvc_launch_count(const genvc_ctx* ctx) { return ctx ? ctx->nlaunch : 0; }
 
-int genvc_debug_tune(genvc_ctx* ctx, int window, int nosync, int l2_ahead_tiles) {
+int genvc_debug_tune(genvc_ctx* ctx, int window, int nosync, int l2_ahead_tiles, int hop_settle_ns, int hop_hold) {
     if (!ctx) return GENVC_E_INVALID;
     if (window > 0) ctx->window = std::min(window, (int)GV_MEGA_NSLOT);
     if (l2_ahead_tiles >= 0) ctx->l2_ahead = l2_ahead_tiles;
+    if (hop_settle_ns >= 0) ctx->hop_settle = hop_settle_ns;
+    if (hop_hold >= 0) ctx->hop_hold = hop_hold;
     ctx->dbg_nosync = nosync ? 1 : 0;
     return GENVC_OK;
 }
@@ -618,7 +620,7 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         p.ids_out = reinterpret_cast<long long*>(ids_out_dev); p.latents_out = latents_out_dev; p.logits_out = logits_out_dev;
         p.status = status_dev;
         p.trace = ctx->trace; p.trace_slots = ctx->trace_slots; p.trace_step = ctx->trace_step;
-        p.window = ctx->window; p.dbg_nosync = ctx->dbg_nosync; p.l2_ahead_tiles = ctx->l2_ahead;
+        p.window = ctx->window; p.dbg_nosync = ctx->dbg_nosync; p.l2_ahead_tiles = ctx->l2_ahead; p.hop_settle_ns = ctx->hop_settle; p.hop_hold = ctx->hop_hold;
         CK(launch_decode_mega(p, ctx->grid, st));
         ctx->nlaunch += 1;
         ctx->n_host = std::min(max_total, ctx->n_host + n_steps);

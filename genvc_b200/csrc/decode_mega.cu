@@ -269,12 +269,18 @@ __device__ __forceinline__ void hop_arrive(unsigned* cnt, int tid) {
     bar_sync(1, MEGA_CONSUMERS);
     if (tid == 0) red_relaxed_add(cnt, 1u);
 }
-__device__ __forceinline__ void hop_wait(const unsigned* cnt, unsigned target, int tid, uint32_t tmask) {
+// `settle_ns`: the arrival counter is bumped without a fence, so it can overtake the last data stores on their way to
+// L2; a first data load that finds a stale tag costs a whole extra round trip, a short pause after the counter
+// reaches its target is cheaper.
+__device__ __forceinline__ void hop_wait(const unsigned* cnt, unsigned target, int tid, uint32_t tmask, unsigned settle_ns,
+                                         volatile int* hold = nullptr) {
     if (tid == 0 && tmask != 0u) {
+        if (hold) *hold = 1;  // the weight producer stops issuing bulk copies: they slow this SM's ordinary loads down
         uint32_t spins = 0;
         while (ld_relaxed_u32(cnt) < target) {
             if (++spins > MEGA_SPIN_LIMIT) __trap();
         }
+        if (settle_ns) __nanosleep(settle_ns);
     }
     bar_sync(1, MEGA_CONSUMERS);
 }
@@ -742,6 +748,7 @@ struct Producer {
     uint32_t land = 0;  // tiles [0, land) have been seen complete (published to the consumers through ring.landed)
     uint32_t window;    // at most this many tiles requested but not landed
     volatile int* stop;
+    volatile int* hold = nullptr;  // non-null: do not issue new copies while *hold != 0 (consumers are polling / loading a hop)
     uint64_t policy;
     __device__ Producer(const Ring& r, volatile int* s, uint32_t w) : ring(r), window(w), stop(s) {
         policy = l2_policy_evict_first();
@@ -761,6 +768,14 @@ struct Producer {
             if (++spins > MEGA_SPIN_LIMIT) __trap();
         }
         if (*stop) return false;
+        if (hold != nullptr) {
+            spins = 0;
+            while (*hold) {
+                advance();
+                if (*stop) return false;
+                if (++spins > MEGA_SPIN_LIMIT) __trap();
+            }
+        }
         spins = 0;
         while (t - land >= window) {  // at most `window` tiles requested but not landed
             advance();
@@ -864,7 +879,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     off += 16 * sizeof(int);
     volatile int* ctl = reinterpret_cast<volatile int*>(smem_raw + off);  // [0] stop flag, [1] tiles consumed, [2] token
     ring.landed = reinterpret_cast<uint32_t*>(smem_raw + off) + 3;        // [3] tiles the producer has seen landed
-    off += 4 * sizeof(int);
+    volatile int* hold = reinterpret_cast<volatile int*>(smem_raw + off) + 4;  // [4] consumers are inside a hop: producer pauses
+    off += 8 * sizeof(int);
     unsigned char* seen = smem_raw + off;  // [Vpad]
 
     if (tid_all == 0) {
@@ -876,6 +892,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
         ctl[1] = 0;
         ctl[2] = 0;
         ctl[3] = 0;
+        ctl[4] = 0;
         mbar_fence_init();
     }
     for (int i = tid_all; i < p.Vpad; i += MEGA_THREADS) seen[i] = p.seen[i];
@@ -893,6 +910,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
         // ================= producer warp =================
         if (tid_all == MEGA_CONSUMERS) {
             Producer pr(ring, ctl, (uint32_t)max(1, min(p.window, NSLOT)));
+            if (p.hop_hold) pr.hold = hold;
             pr.region = p.stream + cta_base(sd, cta);
             pr.region_floats = cta_base(sd, cta + 1) - cta_base(sd, cta);
             pr.ahead_floats = min((long long)p.l2_ahead_tiles * slot_floats(D), pr.region_floats - slot_floats(D));
@@ -943,6 +961,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     const float* mel_emb = p.blob + p.mel_emb_off;
     const float* mel_pos = p.blob + p.mel_pos_off;
     unsigned* const hc = p.hops;
+    const unsigned settle = (unsigned)p.hop_settle_ns;
+    volatile int* const hold_c = p.hop_hold ? hold : nullptr;
     // hop counter targets (counters are zero at launch): x1 / pp / x2 advance by a fixed amount per layer, so they are
     // derived from one layer counter; only the attention target (items vary with S) and the logits target are running sums
     unsigned lc = 0, t_ao = 0, t_lg = 0;
@@ -1000,11 +1020,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     }
 #else
                     } else {
-                        hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask);
+                        hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, settle, hold_c);
                         if (xvalid) ld_tagged_vec<4>(p.x2, 4 * tid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask, &x.x);
                     }
 #endif
                     if (xvalid) *reinterpret_cast<float4*>(xres0 + 4 * tid) = x;
+                    if (hold_c && tid == 0) *hold_c = 0;  // hop data is in registers: the producer may stream again
                     stamp(ts + 0);
                     stats_partial(x, xvalid, shift1, red, lane, warp);
                     bar_sync(1, MEGA_CONSUMERS);
@@ -1040,7 +1061,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                 stamp(ts + 3);
                 // ---- PROJ: merge attention partials -> o ; x1 = x + o . W_proj + b ----
                 {
-                    hop_wait(hc + HC_AO * GV_HOP_STRIDE, t_ao, tid, tmask);
+                    hop_wait(hc + HC_AO * GV_HOP_STRIDE, t_ao, tid, tmask, settle, hold_c);
                     if (xvalid) {
                         const int h = (4 * tid) / HD, d = (4 * tid) % HD;
                         const uint32_t tga = tg + TG_AO;
@@ -1082,6 +1103,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                         }
                         *reinterpret_cast<float4*>(xo + 4 * tid) = make_float4(o0 / den, o1 / den, o2 / den, o3 / den);
                     }
+                    if (hold_c && tid == 0) *hold_c = 0;  // hop data is in registers: the producer may stream again
                     stamp(ts + 4);
                     bar_sync(1, MEGA_CONSUMERS);
                     gemv_dot<NXV>(ring, cs, nun[PH_PROJ], xo, warp, lane, [&](int u, float dot, float c2, float) {
@@ -1095,12 +1117,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                 }
                 // ---- FC + P2: u = gelu_new(LN2(x1) . W_fc + b) (kept in this CTA) -> partial of u . W_proj2 ----
                 {
-                    hop_wait(hc + HC_X1 * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask);
+                    hop_wait(hc + HC_X1 * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c);
                     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (xvalid) {
                         ld_tagged_vec<4>(p.x1, 4 * tid, tg + TG_X1, tmask, &x.x);
                         *reinterpret_cast<float4*>(xres1 + 4 * tid) = x;
                     }
+                    if (hold_c && tid == 0) *hold_c = 0;  // hop data is in registers: the producer may stream again
                     stamp(ts + 6);
                     stats_partial(x, xvalid, shift2, red + 16, lane, warp);
                     bar_sync(1, MEGA_CONSUMERS);
@@ -1133,7 +1156,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     stamp_wait(ts + 13);
                     hop_arrive(hc + HC_PP * GV_HOP_STRIDE, tid);
                     // x2 = x1 + b + sum of the G partials: every CTA reads the finished accumulators itself
-                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask);
+                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c);
                     if (xvalid) {
                         const unsigned long long full_count = (unsigned long long)(G & 0xff);
                         ulonglong2 w0 = ld_x2u64(accl), w1 = ld_x2u64(accl + 2);
@@ -1171,7 +1194,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     float b2 = 0.0f;
                     if (lane == 0) b2 = __ldg(p.blob + p.proj2_b_off + (long long)l * p.layer_stride + cta * 8 + warp);
 #if GV_PP_COUNTER
-                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask);
+                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c);
 #endif
                     stamp(ts + 10);
                     {   // load q: 16 bytes {v, tag, v, tag} of source CTA q / 4, outputs 2 (q % 4), +1; three rounds in flight
@@ -1201,6 +1224,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                                     make_float2(__uint_as_float(a[rr].x), __uint_as_float(a[rr].z));
                         }
                     }
+                    if (hold_c && tid == 0) *hold_c = 0;  // hop data is in registers: the producer may stream again
                     bar_sync(1, MEGA_CONSUMERS);
                     {
                         float s = 0.0f;
@@ -1224,9 +1248,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
 #if GV_ATOMIC_RED
                 lat = xnext;
 #else
-                hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask);
+                hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, settle, hold_c);
                 if (xvalid) ld_tagged_vec<4>(p.x2, 4 * tid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask, &lat.x);
 #endif
+                if (hold_c && tid == 0) *hold_c = 0;
                 stamp(ts + 0);
                 const float* lnp = tile_wait(ring, cs, cs.gt, lane);  // all warps read the parameter tile
                 ln_quad(lat, xvalid, D, lnp, lnp + D, red, tid);
@@ -1242,7 +1267,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                 stamp(ts + 1);
                 hop_arrive(hc + HC_LG * GV_HOP_STRIDE, tid);
                 t_lg += (unsigned)G;
-                hop_wait(hc + HC_LG * GV_HOP_STRIDE, t_lg, tid, tmask);
+                hop_wait(hc + HC_LG * GV_HOP_STRIDE, t_lg, tid, tmask, settle, hold_c);
                 for (int e = 2 * tid; e < p.V; e += 2 * MEGA_CONSUMERS) {
                     if (e + 1 < p.V) {
                         const float2 v = ld_tagged2(p.lg, e, tg, tmask);
@@ -1252,6 +1277,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                         slog[e] = ld_tagged1(p.lg, e, tg, tmask);
                     }
                 }
+                if (hold_c && tid == 0) *hold_c = 0;
                 stamp(ts + 2);
             }
         } else {
@@ -1313,7 +1339,7 @@ size_t mega_smem_bytes(int D, int Vpad) {
     off += MEGA_SCRATCH_BYTES;
     off += (size_t)Vpad * sizeof(float) + 3 * (size_t)D * sizeof(float);
     off += 32 * sizeof(uint64_t);
-    off += (32 + 64 + 16) * sizeof(float) + 16 * sizeof(int) + 4 * sizeof(int);
+    off += (32 + 64 + 16) * sizeof(float) + 16 * sizeof(int) + 8 * sizeof(int);
     off += Vpad;
     return (off + 15) & ~size_t(15);
 }

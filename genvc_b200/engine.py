@@ -279,10 +279,10 @@ class Engine:
         self._check(self.lib.genvc_debug_trace(self._ctx, self._trace.data_ptr(), slots, int(step)))
         return self._trace.view(g, slots)
 
-    def tune(self, window: int = 0, nosync: bool = False, l2_ahead: int = -1):
+    def tune(self, window: int = 0, nosync: bool = False, l2_ahead: int = -1, hop_settle_ns: int = -1, hop_hold: int = -1):
         """Fused-kernel knobs: TMA tiles in flight per SM; ``nosync`` = streaming-rate probe (garbage results);
         ``l2_ahead`` = HBM->L2 prefetch distance in tiles (-1 keeps the current value)."""
-        self._check(self.lib.genvc_debug_tune(self._ctx, int(window), int(bool(nosync)), int(l2_ahead)))
+        self._check(self.lib.genvc_debug_tune(self._ctx, int(window), int(bool(nosync)), int(l2_ahead), int(hop_settle_ns), int(hop_hold)))
 
     # ------------------------------------------------------------------ microbenchmark
     def kv_attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S: int) -> torch.Tensor:

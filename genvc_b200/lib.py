@@ -69,7 +69,7 @@ SIGNATURES = {
     "genvc_kv_attention": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "genvc_launch_count": (C.c_uint64, [_P]),
     "genvc_debug_trace": (C.c_int, [_P, _P, C.c_int, C.c_int]),
-    "genvc_debug_tune": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
+    "genvc_debug_tune": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
 }
 
 _lib = None
