@@ -407,7 +407,14 @@ __device__ __forceinline__ void ln_quad(float4& x, bool valid, int D, const floa
 // epi(u, dot, c2, c1) with  dot = sum_k x_k W'[k][unit]  and the unit's two epilogue constants
 // (pack_stream_kernel).
 // ---------------------------------------------------------------------------------------------
-template <int NXV, class Epi>
+// EARLY: release every tile right after its unit (the producer refills while this phase goes on: needed when another
+// GEMV follows without a hop, i.e. FC -> P2); otherwise one release for all of the warp's tiles at the end (each
+// __syncwarp + elected mbarrier.arrive costs ~250 cycles of this warp's chain).
+// Known limit (measured): ptxas sinks every LDS.128 next to its FFMAs (one or two shared-memory loads in
+// flight per warp); forcing 8-deep batches needs ~64 more registers than the 168 this kernel has (tried: explicit double
+// buffer -> spills, __noinline__ core -> ~724 B of caller-saved register traffic per call, setmaxnreg 232 -> still
+// allocated at 168): all slower.
+template <int NXV, bool EARLY, class Epi>
 __device__ __forceinline__ void gemv_dot(const Ring& ring, const Cons& cs, int nunits, const float* xs, int warp, int lane,
                                          Epi epi) {
     constexpr int D = NXV * 128, UF = D + 4;
@@ -438,8 +445,11 @@ __device__ __forceinline__ void gemv_dot(const Ring& ring, const Cons& cs, int n
             }
             tot[k] = (a0 + a1) + (a2 + a3);
         }
-        if (t < ntiles) tile_release(ring, cs.gt + (uint32_t)t, lane);  // early: the producer refills while we go on
+        if constexpr (EARLY) {
+            if (t < ntiles) tile_release(ring, cs.gt + (uint32_t)t, lane);
+        }
     }
+    if constexpr (!EARLY) group_release(ring, cs, g, ntiles, lane);
     // transposing butterfly: lanes [8q, 8q+8) end up reducing tot[q]
     const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
     const float k0 = up16 ? tot[2] : tot[0], s0 = up16 ? tot[0] : tot[2];
@@ -1033,7 +1043,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     stats_finish(red, inv_d, shift1, mean, rstd);
                     shift1 = mean;
                     stamp(ts + 1);
-                    gemv_dot<NXV>(ring, cs, nun[PH_QKV], xres0, warp, lane, [&](int u, float dot, float c2, float c1) {
+                    gemv_dot<NXV, false>(ring, cs, nun[PH_QKV], xres0, warp, lane, [&](int u, float dot, float c2, float c1) {
                         st_tagged(p.xq, ubeg[PH_QKV] + u, fmaf(rstd, fmaf(-mean, c1, dot), c2), tg + TG_XQ);
                     });
                     cs.gt += (uint32_t)ntl[PH_QKV];
@@ -1106,7 +1116,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     if (hold_c && tid == 0) *hold_c = 0;  // hop data is in registers: the producer may stream again
                     stamp(ts + 4);
                     bar_sync(1, MEGA_CONSUMERS);
-                    gemv_dot<NXV>(ring, cs, nun[PH_PROJ], xo, warp, lane, [&](int u, float dot, float c2, float) {
+                    gemv_dot<NXV, false>(ring, cs, nun[PH_PROJ], xo, warp, lane, [&](int u, float dot, float c2, float) {
                         const int col = ubeg[PH_PROJ] + u;
                         st_tagged(p.x1, col, xres0[col] + (dot + c2), tg + TG_X1);
                     });
@@ -1131,7 +1141,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     stats_finish(red + 16, inv_d, shift2, mean, rstd);
                     shift2 = mean;
                     stamp(ts + 7);
-                    gemv_dot<NXV>(ring, cs, nun[PH_FC], xres1, warp, lane, [&](int u, float dot, float c2, float c1) {
+                    gemv_dot<NXV, true>(ring, cs, nun[PH_FC], xres1, warp, lane, [&](int u, float dot, float c2, float c1) {
                         us[u] = gelu_new(fmaf(rstd, fmaf(-mean, c1, dot), c2));
                     });
                     cs.gt += (uint32_t)ntl[PH_FC];
@@ -1261,7 +1271,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                 bar_sync(1, MEGA_CONSUMERS);
                 if (warp == 0) tile_release(ring, cs.gt, lane, 4u);
                 cs.gt += 1u;
-                gemv_dot<NXV>(ring, cs, nun[PH_HEAD], xo, warp, lane,
+                gemv_dot<NXV, false>(ring, cs, nun[PH_HEAD], xo, warp, lane,
                               [&](int u, float dot, float c2, float) { st_tagged(p.lg, ubeg[PH_HEAD] + u, dot + c2, tg); });
                 cs.gt += (uint32_t)ntl[PH_HEAD];
                 stamp(ts + 1);
