@@ -408,11 +408,17 @@ static int run_blocks(genvc_ctx* ctx, int B, int M, int pos0, const int* skip, c
         const LayerOff& o = ctx->layout.layers[l];
         float* kc = ctx->kv + ((size_t)l * 2 + 0) * ctx->kv_plane();
         float* vc = ctx->kv + ((size_t)l * 2 + 1) * ctx->kv_plane();
-        CK(launch_layernorm(X, D, 0, A, D, 0, R, R, D, ctx->w(o.ln1_w), ctx->w(o.ln1_b), nullptr, nullptr, skip, st, nl));
-        CK(launch_gemm(gemm(A, D, ctx->w(o.attn_w), 3 * D, 0, ctx->w(o.attn_b), nullptr, 0, QKV, 3 * D, R, 3 * D, D, ACT_NONE),
-                       sk, kSplitKFloats, skip, st, nl));
-        if (pos0 >= 0)
-            CK(launch_kv_scatter(QKV, B, M, D, H, kc, vc, (long)ctx->kv_batch_stride(), g.max_seq, pos0, skip, st, nl));
+        // ln_1: first layer only; afterwards it rides in the epilogue of the previous block's mlp.c_proj GEMM
+        if (l == 0)
+            CK(launch_layernorm(X, D, 0, A, D, 0, R, R, D, ctx->w(o.ln1_w), ctx->w(o.ln1_b), nullptr, nullptr, skip, st, nl));
+        {   // [q|k|v] projection; the K/V cache append rides in its epilogue
+            GemmArgs q = gemm(A, D, ctx->w(o.attn_w), 3 * D, 0, ctx->w(o.attn_b), nullptr, 0, QKV, 3 * D, R, 3 * D, D, ACT_NONE);
+            if (pos0 >= 0) {
+                q.kv_k = kc; q.kv_v = vc; q.kv_bs = (long)ctx->kv_batch_stride(); q.kv_rows = M; q.kv_H = H; q.kv_S_max = g.max_seq;
+                q.kv_pos0 = pos0;
+            }
+            CK(launch_gemm(q, sk, kSplitKFloats, skip, st, nl));
+        }
         if (pos0 >= 0 && M == 1) {
             // single-token decode against the cache (positions 0..pos0)
             CK(launch_kv_attention(QKV, 3L * D, kc, vc, (long)ctx->kv_batch_stride(), B, H, hd, pos0 + 1, g.max_seq, A, D, skip,
@@ -426,13 +432,21 @@ static int run_blocks(genvc_ctx* ctx, int B, int M, int pos0, const int* skip, c
             a.B = B; a.H = H; a.M = M; a.hd = hd; a.n_keys = M; a.causal = 1; a.pos0 = 0; a.scale = scale;
             CK(launch_attention(a, skip, st, nl));
         }
-        CK(launch_gemm(gemm(A, D, ctx->w(o.proj_w), D, 0, ctx->w(o.proj_b), X, D, X, D, R, D, D, ACT_NONE), sk, kSplitKFloats,
-                       skip, st, nl));
-        CK(launch_layernorm(X, D, 0, A, D, 0, R, R, D, ctx->w(o.ln2_w), ctx->w(o.ln2_b), nullptr, nullptr, skip, st, nl));
+        {   // attention output projection + residual; ln_2 of the result rides in the epilogue
+            GemmArgs pj = gemm(A, D, ctx->w(o.proj_w), D, 0, ctx->w(o.proj_b), X, D, X, D, R, D, D, ACT_NONE);
+            pj.ln_w = ctx->w(o.ln2_w); pj.ln_b = ctx->w(o.ln2_b); pj.ln_out = A; pj.ld_ln = D;
+            CK(launch_gemm(pj, sk, kSplitKFloats, skip, st, nl));
+        }
         CK(launch_gemm(gemm(A, D, ctx->w(o.fc_w), 4 * D, 0, ctx->w(o.fc_b), nullptr, 0, U, 4 * D, R, 4 * D, D, ACT_GELU_NEW), sk,
                        kSplitKFloats, skip, st, nl));
-        CK(launch_gemm(gemm(U, 4 * D, ctx->w(o.proj2_w), D, 0, ctx->w(o.proj2_b), X, D, X, D, R, D, 4 * D, ACT_NONE), sk,
-                       kSplitKFloats, skip, st, nl));
+        {   // mlp.c_proj + residual; the next block's ln_1 rides in the epilogue
+            GemmArgs p2 = gemm(U, 4 * D, ctx->w(o.proj2_w), D, 0, ctx->w(o.proj2_b), X, D, X, D, R, D, 4 * D, ACT_NONE);
+            if (l + 1 < g.n_layer) {
+                const LayerOff& nx = ctx->layout.layers[l + 1];
+                p2.ln_w = ctx->w(nx.ln1_w); p2.ln_b = ctx->w(nx.ln1_b); p2.ln_out = A; p2.ld_ln = D;
+            }
+            CK(launch_gemm(p2, sk, kSplitKFloats, skip, st, nl));
+        }
     }
     return GENVC_OK;
 }

@@ -153,7 +153,86 @@ __global__ void splitk_epilogue_kernel(GemmArgs a, const float* __restrict__ ws,
         if (a.act == ACT_GELU_NEW) v = gelu_new(v);
         if (a.residual) v += a.residual[(size_t)m * a.ldr + n];
         a.C[(size_t)m * a.ldc + n] = v;
+        if (a.kv_k != nullptr) {  // fused K/V cache append (what kv_scatter_kernel does from the finished rows)
+            const int Dkv = a.N / 3;
+            if (n >= Dkv) {
+                const int c = (n - Dkv) % Dkv, hd = Dkv / a.kv_H;
+                const int b = m / a.kv_rows, r = m % a.kv_rows;
+                float* dst = (n < 2 * Dkv) ? a.kv_k : a.kv_v;
+                dst[(size_t)b * a.kv_bs + ((size_t)(c / hd) * a.kv_S_max + a.kv_pos0 + r) * hd + (c % hd)] = v;
+            }
+        }
     }
+}
+
+// split-K reduction + bias + residual of one row per block (thread = 4 columns, all split loads in flight), then
+// LayerNorm of that row (two-pass, like layernorm_kernel).  N = D <= 1024.
+__global__ void __launch_bounds__(256) splitk_ln_epilogue_kernel(GemmArgs a, const float* __restrict__ ws, int splits, const int* skip) {
+    if (skip && *skip) return;
+    __shared__ float red[2][8];
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = tid * 4;
+    const bool valid = n < a.N;
+    const size_t total = (size_t)a.M * a.N;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+        const float* src = ws + (size_t)row * a.N + n;
+        int z = 0;
+        for (; z + 4 <= splits; z += 4) {  // four independent loads in flight, summed in split order
+            const float4 t0 = *reinterpret_cast<const float4*>(src + (size_t)(z + 0) * total);
+            const float4 t1 = *reinterpret_cast<const float4*>(src + (size_t)(z + 1) * total);
+            const float4 t2 = *reinterpret_cast<const float4*>(src + (size_t)(z + 2) * total);
+            const float4 t3 = *reinterpret_cast<const float4*>(src + (size_t)(z + 3) * total);
+            acc.x += t0.x; acc.y += t0.y; acc.z += t0.z; acc.w += t0.w;
+            acc.x += t1.x; acc.y += t1.y; acc.z += t1.z; acc.w += t1.w;
+            acc.x += t2.x; acc.y += t2.y; acc.z += t2.z; acc.w += t2.w;
+            acc.x += t3.x; acc.y += t3.y; acc.z += t3.z; acc.w += t3.w;
+        }
+        for (; z < splits; ++z) {
+            const float4 t = *reinterpret_cast<const float4*>(src + (size_t)z * total);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        if (a.bias) {
+            const float4 b = *reinterpret_cast<const float4*>(a.bias + n);
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+        }
+        if (a.act == ACT_GELU_NEW) {
+            acc.x = gelu_new(acc.x); acc.y = gelu_new(acc.y); acc.z = gelu_new(acc.z); acc.w = gelu_new(acc.w);
+        }
+        if (a.residual) {
+            const float4 r = *reinterpret_cast<const float4*>(a.residual + (size_t)row * a.ldr + n);
+            acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+        }
+        *reinterpret_cast<float4*>(a.C + (size_t)row * a.ldc + n) = acc;
+    }
+    float s = valid ? ((acc.x + acc.y) + (acc.z + acc.w)) : 0.0f;
+    s = warp_sum(s);
+    if (lane == 0) red[0][warp] = s;
+    __syncthreads();
+    float tot = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[0][w];
+    const float mean = tot / (float)a.N;
+    const float d0 = acc.x - mean, d1 = acc.y - mean, d2 = acc.z - mean, d3 = acc.w - mean;
+    float q = valid ? (fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3)) : 0.0f;
+    q = warp_sum(q);
+    if (lane == 0) red[1][warp] = q;
+    __syncthreads();
+    float qt = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) qt += red[1][w];
+    const float rstd = 1.0f / sqrtf(qt / (float)a.N + 1e-5f);
+    if (valid) {
+        const float4 ww = *reinterpret_cast<const float4*>(a.ln_w + n);
+        const float4 bb = *reinterpret_cast<const float4*>(a.ln_b + n);
+        *reinterpret_cast<float4*>(a.ln_out + (size_t)row * a.ld_ln + n) =
+            make_float4(d0 * rstd * ww.x + bb.x, d1 * rstd * ww.y + bb.y, d2 * rstd * ww.z + bb.z, d3 * rstd * ww.w + bb.w);
+    }
+}
+static bool launch_splitk_ln(const GemmArgs& a, const float* ws, int splits, const int* skip, cudaStream_t st) {
+    if ((a.N & 3) || a.N > 1024 || (a.ldc & 3) || (a.ldr & 3) || (a.ld_ln & 3)) return false;
+    splitk_ln_epilogue_kernel<<<a.M, 256, 0, st>>>(a, ws, splits, skip);
+    return true;
 }
 
 // GENVC_TC=0 in the environment keeps every GEMM on the fp32 CUDA-core kernel (debug / A-B comparison)
@@ -166,6 +245,46 @@ static bool use_tensor_cores() {
     return v == 1;
 }
 
+// forward declarations of the follow-up launchers used below
+cudaError_t launch_kv_scatter(const float* qkv, int B, int M, int D, int H, float* kcache, float* vcache, long batch_stride,
+                              int S_max, int pos0, const int* skip, cudaStream_t st, unsigned long long* nlaunch);
+
+// follow-ups that could not be fused into a split-K epilogue: separate launches from the finished C
+static cudaError_t gemm_followups(const GemmArgs& a, bool ln_done, bool kv_done, const int* skip, cudaStream_t st,
+                                  unsigned long long* nlaunch) {
+    if (a.ln_w && !ln_done) {
+        cudaError_t e = launch_layernorm(a.C, a.ldc, 0, a.ln_out, a.ld_ln, 0, a.M, a.M, a.N, a.ln_w, a.ln_b, nullptr, nullptr, skip, st,
+                                         nlaunch);
+        if (e != cudaSuccess) return e;
+    }
+    if (a.kv_k && !kv_done) {
+        const int Dkv = a.N / 3;
+        if (a.ldc != a.N) return cudaErrorInvalidValue;
+        cudaError_t e = launch_kv_scatter(a.C, a.M / a.kv_rows, a.kv_rows, Dkv, a.kv_H, a.kv_k, a.kv_v, a.kv_bs, a.kv_S_max, a.kv_pos0, skip,
+                                          st, nlaunch);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// split-K reduction (+ fused LayerNorm / KV append when requested)
+static cudaError_t run_splitk_epilogue(const GemmArgs& a, const float* ws, int splits, const int* skip, cudaStream_t st,
+                                       unsigned long long* nlaunch) {
+    bool ln_done = false, kv_done = false;
+    if (a.ln_w && !a.kv_k && launch_splitk_ln(a, ws, splits, skip, st)) {
+        ln_done = true;
+    } else {
+        size_t total = (size_t)a.M * a.N;
+        int blocks = (int)min((size_t)1184, (total + 255) / 256);
+        splitk_epilogue_kernel<<<blocks, 256, 0, st>>>(a, ws, splits, skip);
+        kv_done = a.kv_k != nullptr;
+    }
+    GV_BUMP(nlaunch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return gemm_followups(a, ln_done, kv_done, skip, st, nlaunch);
+}
+
 cudaError_t launch_gemm(const GemmArgs& a, float* ws, size_t ws_floats, const int* skip, cudaStream_t st,
                         unsigned long long* nlaunch) {
     if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaErrorInvalidValue;
@@ -176,13 +295,8 @@ cudaError_t launch_gemm(const GemmArgs& a, float* ws, size_t ws_floats, const in
         cudaError_t e = launch_gemm_tc(a, ws, ws_floats, skip, st, &splits);
         if (e != cudaSuccess) return e;
         GV_BUMP(nlaunch);
-        if (splits > 1) {
-            size_t total = (size_t)a.M * a.N;
-            int blocks = (int)min((size_t)1184, (total + 255) / 256);
-            splitk_epilogue_kernel<<<blocks, 256, 0, st>>>(a, ws, splits, skip);
-            GV_BUMP(nlaunch);
-        }
-        return cudaGetLastError();
+        if (splits > 1) return run_splitk_epilogue(a, ws, splits, skip, st, nlaunch);
+        return gemm_followups(a, false, false, skip, st, nlaunch);
     }
     const int BM = a.M <= 16 ? 16 : (a.M <= 32 ? 32 : 64);
     dim3 grid((a.N + 63) / 64, (a.M + BM - 1) / BM, 1);
@@ -204,13 +318,10 @@ cudaError_t launch_gemm(const GemmArgs& a, float* ws, size_t ws_floats, const in
     else if (BM == 32) gemm_kernel<32><<<grid, 256, 0, st>>>(a, ws, k_chunk, skip);
     else gemm_kernel<64><<<grid, 256, 0, st>>>(a, ws, k_chunk, skip);
     GV_BUMP(nlaunch);
-    if (splits > 1) {
-        size_t total = (size_t)a.M * a.N;
-        int blocks = (int)min((size_t)1184, (total + 255) / 256);
-        splitk_epilogue_kernel<<<blocks, 256, 0, st>>>(a, ws, splits, skip);
-        GV_BUMP(nlaunch);
-    }
-    return cudaGetLastError();
+    if (splits > 1) return run_splitk_epilogue(a, ws, splits, skip, st, nlaunch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return gemm_followups(a, false, false, skip, st, nlaunch);
 }
 
 // =============================================================================================

@@ -24,6 +24,18 @@ struct GemmArgs {
     int ldc;
     int M, N, K;
     int act;
+    // optional fused follow-ups (launch_gemm runs them in the split-K epilogue when it can, else as separate launches):
+    //   LayerNorm of the finished rows (N == D <= 1024): ln_out[m, :] = LN(C[m, :]; ln_w, ln_b)
+    const float* ln_w = nullptr;
+    const float* ln_b = nullptr;
+    float* ln_out = nullptr;
+    int ld_ln = 0;
+    //   K/V cache append of a [q|k|v] projection (N == 3 D_kv): columns [D_kv, 3 D_kv) of row (b, i) also go to
+    //   kv_{k,v} + b * kv_bs + ((col / hd) * S_max + pos0 + i) * hd + col % hd
+    float* kv_k = nullptr;
+    float* kv_v = nullptr;
+    long kv_bs = 0;
+    int kv_rows = 0, kv_H = 0, kv_S_max = 0, kv_pos0 = 0;
 };
 
 struct AttnArgs {
