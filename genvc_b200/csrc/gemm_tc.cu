@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(GemmArgs a, const f
 
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(&full[s], LOADERS + 1);  // 128 loader arrivals + the producer's expect_tx arrival
+            mbar_init(&full[s], 4 + 1);  // one arrival per loader warp + the producer's expect_tx arrival
             mbar_init(&empty[s], 1);
         }
         mbar_init(done, 1);
@@ -208,20 +208,29 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(GemmArgs a, const f
                 if (cur < nst) {
                     if (cur + 1 < nst) load_stage(cur + 1, va[h ^ 1]);
                     const int s = cur % C::STAGES;
-                    mbar_wait(&empty[s], (((uint32_t)(cur / C::STAGES)) & 1u) ^ 1u);
+                    if (lane == 0) mbar_wait(&empty[s], (((uint32_t)(cur / C::STAGES)) & 1u) ^ 1u);  // one poller per warp
+                    __syncwarp();
                     store_stage(s, va[h]);
                     fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-                    mbar_arrive(&full[s]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[s]);
                 }
             }
         }
         // ================= epilogue: lane = output column, register = row =================
-        mbar_wait(done, 0u);
+        if (lane == 0) mbar_wait(done, 0u);
+        __syncwarp();
         tc_fence_after();
         const int n = n0 + 32 * warp + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
-        const size_t total = (size_t)a.M * a.N;
         const float bias = (a.bias && n < a.N) ? a.bias[n] : 0.0f;
+        const int mrem = a.M - m0;  // valid rows of this chunk
+        // compact address arithmetic (one pointer bump per row): the unrolled epilogue is the largest piece of code in
+        // this short kernel and its instruction fetch showed up as the top stall
+        float* out = (gridDim.z > 1) ? ws + (size_t)blockIdx.z * ((size_t)a.M * a.N) + (size_t)m0 * a.N + n : a.C + (size_t)m0 * a.ldc + n;
+        const float* res = a.residual ? a.residual + (size_t)m0 * a.ldr + n : nullptr;
+        const int ostride = (gridDim.z > 1) ? a.N : a.ldc;
+        const bool direct = gridDim.z == 1;
 #pragma unroll
         for (int h = 0; h < MP / 32; ++h) {
             float v[32];
@@ -229,17 +238,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(GemmArgs a, const f
             if (n < a.N) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const int m = m0 + 32 * h + i;
-                    if (m < a.M) {
-                        if (gridDim.z > 1) {
-                            ws[(size_t)blockIdx.z * total + (size_t)m * a.N + n] = v[i];
-                        } else {
-                            float y = v[i] + bias;
+                    if (32 * h + i < mrem) {
+                        float y = v[i];
+                        if (direct) {
+                            y += bias;
                             if (a.act == ACT_GELU_NEW) y = gelu_new(y);
-                            if (a.residual) y += a.residual[(size_t)m * a.ldr + n];
-                            a.C[(size_t)m * a.ldc + n] = y;
+                            if (res) y += res[0];
                         }
+                        out[0] = y;
                     }
+                    out += ostride;
+                    if (res) res += a.ldr;
                 }
             }
         }
