@@ -136,7 +136,10 @@ template <int MP>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(GemmArgs a, const float* __restrict__ Wt, float* __restrict__ ws,
                                                              int k_chunk, const int* skip) {
     using C = Cfg<MP>;
-    if (skip && *skip) return;
+    if (skip) {  // (the flag is written by an earlier kernel of the stream)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (*skip) return;
+    }
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -200,6 +203,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(GemmArgs a, const f
                 *reinterpret_cast<float4*>(sx_lo + o) = lo;
             }
         };
+        // Programmatic dependent launch: this grid may start while the preceding (small) kernel still runs — barrier setup,
+        // TMEM allocation and the weight producer's first stages overlap it; everything that reads or overwrites data of
+        // earlier kernels (activations, residual, split-K workspace) comes after this wait.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         if (nst > 0) load_stage(0, va[0]);
         for (int it = 0; it < nst; it += 2) {
 #pragma unroll
@@ -376,10 +383,19 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, float* ws, size_t ws_floats, const
         splits = (a.K + k_chunk - 1) / k_chunk;
     }
     grid.z = splits;
-    if (MP == 64) tc::gemm_tc_kernel<64><<<grid, tc::THREADS, tc::Cfg<64>::SMEM_BYTES, st>>>(a, Wt, ws, k_chunk, skip);
-    else tc::gemm_tc_kernel<128><<<grid, tc::THREADS, tc::Cfg<128>::SMEM_BYTES, st>>>(a, Wt, ws, k_chunk, skip);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = MP == 64 ? tc::Cfg<64>::SMEM_BYTES : tc::Cfg<128>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     *splits_out = splits;
-    return cudaGetLastError();
+    if (MP == 64) return cudaLaunchKernelEx(&cfg, tc::gemm_tc_kernel<64>, a, Wt, ws, k_chunk, skip);
+    return cudaLaunchKernelEx(&cfg, tc::gemm_tc_kernel<128>, a, Wt, ws, k_chunk, skip);
 }
 
 }  // namespace gv

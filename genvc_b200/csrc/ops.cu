@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs a, float* __restrict
 }
 
 __global__ void splitk_epilogue_kernel(GemmArgs a, const float* __restrict__ ws, int splits, const int* skip) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a following tcgen05 GEMM may begin its prologue / weight prefetch
     if (skip && *skip) return;
     const size_t total = (size_t)a.M * a.N;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -168,6 +169,7 @@ __global__ void splitk_epilogue_kernel(GemmArgs a, const float* __restrict__ ws,
 // split-K reduction + bias + residual of one row per block (thread = 4 columns, all split loads in flight), then
 // LayerNorm of that row (two-pass, like layernorm_kernel).  N = D <= 1024.
 __global__ void __launch_bounds__(256) splitk_ln_epilogue_kernel(GemmArgs a, const float* __restrict__ ws, int splits, const int* skip) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a following tcgen05 GEMM may begin its prologue / weight prefetch
     if (skip && *skip) return;
     __shared__ float red[2][8];
     const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
