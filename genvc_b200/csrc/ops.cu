@@ -336,6 +336,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
                                                         int rpg, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, const float* __restrict__ w2,
                                                         const float* __restrict__ b2, const int* skip) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a following tcgen05 GEMM may begin its prologue / weight prefetch
     if (skip && *skip) return;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -423,6 +424,7 @@ cudaError_t launch_rmsnorm(const float* X, float* Y, int rows, int D, const floa
 // =============================================================================================
 template <int HD>
 __global__ void __launch_bounds__(256) attention_kernel(AttnArgs a, const int* skip) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a following tcgen05 GEMM may begin its prologue / weight prefetch
     if (skip && *skip) return;
     constexpr int QT = 8, KT = 32, LD = HD + 4, DPL = HD / 32;
     extern __shared__ __align__(16) float sm[];
