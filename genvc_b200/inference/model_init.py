@@ -71,6 +71,32 @@ class GenVCModel:
         return self.get_gpt_cond_latents_from_mels(mels)
 
     @torch.inference_mode()
+    def inference(self, src_audio: torch.Tensor, cond_latent: torch.Tensor, do_sample: bool = True, top_p: float = 0.85,
+                  top_k: int = 15, temperature: float = 0.75, num_beams: int = 1, length_penalty: float = 1.0,
+                  repetition_penalty: float = 10.0, output_attentions: bool = False,
+                  reuse_decode_latents: bool = False) -> torch.Tensor:
+        """One source segment -> waveform (``trainers/hifigan_trainer.py:458-504``): content codes, ``gpt.generate``,
+        EOS stripped, latents of the generated codes, x``hifigan_scale_factor`` linear interpolation, vocoder.
+        ``reuse_decode_latents``: take the latents the decode kernel emitted instead of the teacher-forced second
+        pass (equal up to fp32 rounding)."""
+        feat = self.content_extractor.extract_content_features(src_audio)
+        codes = self.content_dvae.get_codebook_indices(feat.transpose(1, 2))
+        gen = self.gpt.generate(cond_latent, codes, do_sample=do_sample, top_p=top_p, top_k=top_k, temperature=temperature,
+                                num_beams=num_beams, length_penalty=length_penalty, repetition_penalty=repetition_penalty,
+                                output_attentions=output_attentions)[0]
+        keep = (gen != self.gpt.stop_audio_token).nonzero().squeeze()
+        if reuse_decode_latents:
+            lat = self.gpt.last_latents[0][keep].reshape(1, -1, self.gpt.last_latents.shape[-1])
+        else:
+            gen = gen[keep]
+            out_len = torch.tensor([gen.shape[-1] * self.config.model_args.gpt_code_stride_len], device=self.device)
+            content_len = torch.tensor([codes.shape[-1]], device=self.device)
+            lat = self.gpt(codes, content_len, gen.unsqueeze(0), out_len, cond_latents=cond_latent, return_latent=True)
+        mel_input = torch.nn.functional.interpolate(lat.transpose(1, 2), scale_factor=[self.hifigan_scale_factor],
+                                                    mode="linear").squeeze(1)
+        return self.hifigan(mel_input)
+
+    @torch.inference_mode()
     def get_gpt_cond_latents_from_mels(self, mel_chunks) -> torch.Tensor:
         """Same, entered after the mel front-end: list of [B, 80, S_i] (or [B, 1, 80, S_i])."""
         if not mel_chunks:
