@@ -127,6 +127,37 @@ def test_teacher_forced_logits(name, mode, cuda_device):
     assert ok, f"latent max err {err}"
 
 
+@pytest.mark.parametrize("name,T,n", [("toy_d128_greedy", 400, 600), ("toy_d256_h4_greedy", 400, 600),
+                                      ("toy_d512_h2_greedy", 300, 200), ("full_h4_cfg1", 240, 40), ("full_h16_greedy", 300, 24)])
+def test_fused_long_context_matches_per_op(name, T, n, cuda_device):
+    """Long prefixes (S up to ~1035 of S_max = 1088): the fused kernel's attention items span several 32-key blocks
+    and up to 8 key ranges per head.  Forced random tokens; fused logits / latents against the per-op path (whose
+    attention kernel is checked against torch at S = 333 and whose GEMMs are pinned by the fixtures)."""
+    fx = load_golden(name)
+    g = make_gpt(fx, cuda_device)
+    eng = g.engine
+    from genvc_b200.engine import Sampling
+
+    gen = torch.Generator().manual_seed(99)
+    codes = torch.randint(0, 256, (1, T), generator=gen).to(cuda_device)
+    cond = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device)
+    forced = torch.randint(0, 1024, (n, 1), generator=gen).to(cuda_device)
+    sp = Sampling(**fx["sampling"], max_new_tokens=n)
+    out = {}
+    for mode in (1, 2):
+        g.compute_embeddings(cond, codes)
+        eng.prefill(g._prefix)
+        ch = eng.decode(n, sp, forced=forced, want_logits=True, mode=mode)
+        emitted, _ = ch.status.tolist()
+        assert emitted == n
+        assert torch.equal(ch.ids.cpu(), forced.cpu())
+        out[mode] = (ch.logits.clone(), ch.latents.clone())
+    ok, err = close(out[2][0], out[1][0], LOGIT_ATOL, LOGIT_RTOL)
+    assert ok, f"logit max err {err}"
+    ok, err = close(out[2][1], out[1][1], LAT_ATOL, LAT_RTOL)
+    assert ok, f"latent max err {err}"
+
+
 @pytest.mark.parametrize("name", FULL)
 def test_full_size_token_ids_bit_exact(name, cuda_device):
     """BASELINE configs[0] and friends at L=30, D=1024: free-running ids through the fused kernel."""
