@@ -506,21 +506,21 @@ __device__ __forceinline__ void gemv_outer(const Ring& ring, const Cons& cs, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// single-query attention over one (head, key range) item, 8 warps, built for a short dependency
-// chain.  Arithmetic of HF GPT2Attention._attn for q_len == 1:
+// single-query attention over one (head, key range) item, 8 warps, built for a short dependency chain after q
+// arrives.  Arithmetic of HF GPT2Attention._attn for q_len == 1:
 //   s_j = (q . k_j) / sqrt(hd);  p = softmax_j(s);  o = sum_j p_j v_j       (un-normalised here)
-//   * before the hop wait for q: K rows of the first 32 keys (warp w: rows w, w + 8, w + 16, w + 24)
-//     and the V elements of the first 32 keys (thread (ks, d) = (tid / HD, tid % HD): keys ks,
-//     ks + NS, ...) are requested from the cache;
-//   * after it: q (every warp), and for the position being decoded k/v of this very step from the
-//     exchange buffer (appended to the cache by the threads that hold them);
-//   * scores: one warp per key, dot + shuffle tree -> shared memory; barrier;
-//   * every warp computes the softmax weights of all (<= 160) keys redundantly (lane l: keys l,
-//     l + 32, ...), so p_j reaches the PV threads by a shuffle, not a barrier;
-//   * PV: thread (ks, d) accumulates its keys; the NS = 256 / HD partials meet in shared memory.
+//   * keys are cut into batches of 32: warp w owns rows 4w .. 4w+3 of every batch and keeps its own running
+//     (max, sum, o[hd]) -- flash-decoding inside the CTA: no score buffer, no barrier before the softmax;
+//   * before q exists: K and V rows of batch 0 are requested from the cache into registers;
+//   * then every warp polls the tagged q words (only the <= H * 8 attention CTAs read xq, so they poll the data
+//     directly: one L2 round trip less than counter-then-data); the warp that owns the position being decoded also
+//     polls k / v of this very step from the exchange buffer and appends them to the cache; that position rides along
+//     as a fifth row of its batch (its cache row is loaded as zeros and masked);
+//   * per batch: 4 (+1) dots and one interleaved shuffle tree, online-softmax update, o += p v; K / V rows of the next
+//     batch are requested as soon as the registers of the current one are free;
+//   * the 8 per-warp partials meet in shared memory behind ONE barrier and are merged by thread d < hd.
 // ---------------------------------------------------------------------------------------------
-#define ATT_MAX_BLOCKS 5  // 32-key blocks per item (att_chunk(S) <= 160)
-#define ATT_ROWS 4        // K rows per warp per block (32 keys / 8 warps)
+#define ATT_ROWS 4        // K rows per warp per batch (32 keys / 8 warps)
 template <int HD>
 struct AttLane {
     static constexpr int VEC = (HD >= 128) ? 4 : (HD / 32);  // floats per lane per chunk
@@ -545,203 +545,199 @@ __device__ __forceinline__ void st_vec(float* p, const float* r) {
     else if constexpr (VEC == 2) __stcg(reinterpret_cast<float2*>(p), make_float2(r[0], r[1]));
     else __stcg(p, r[0]);
 }
+// DPL tagged elements of one lane (element e at base[2e] = {value, tag}); false while any tag is stale
+template <int VEC, int NCH>
+__device__ __forceinline__ bool ld_tagged_lane(const float* base, int lane, uint32_t tag, uint32_t tmask, float* r) {
+    bool ok = true;
+    if constexpr (VEC == 1) {
+        const uint2 a = ld_x8(base + 2 * lane);
+        ok = ((a.y ^ tag) & tmask) == 0u;
+        r[0] = __uint_as_float(a.x);
+    } else {
+        uint4 a[NCH * (VEC / 2)];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int w2 = 0; w2 < VEC / 2; ++w2) a[c * (VEC / 2) + w2] = ld_x16(base + 2 * ((c * 32 + lane) * VEC + 2 * w2));
+#pragma unroll
+        for (int w2 = 0; w2 < NCH * (VEC / 2); ++w2) {
+            ok = ok && tags_ok(a[w2], tag, tmask);
+            r[2 * w2] = __uint_as_float(a[w2].x);
+            r[2 * w2 + 1] = __uint_as_float(a[w2].z);
+        }
+    }
+    return ok;
+}
 
 template <int HD, bool DBG>
 __device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict__ Vc, const float* xq, int D, int h, int j0, int j1, int S,
-                         uint32_t tag_in, const unsigned* cnt_in, unsigned target_in, float* sc, float* opart, int tid,
+                         uint32_t tag_in, float* wml, float* wpart, int tid,
                          float* o_out, float* ml_out, int item, uint32_t tag_out, uint32_t tmask, unsigned long long* dbg) {
     using L = AttLane<HD>;
     long long ck[8];
     if constexpr (DBG) ck[0] = clock64();
     constexpr int VEC = L::VEC, NCH = L::NCH, DPL = L::DPL;
-    constexpr int DV = HD / 4;               // PV stage: a thread owns 4 consecutive dims, DV threads cover a key
-    constexpr int NS = MEGA_CONSUMERS / DV;  // key slices of the PV stage
-    constexpr int VPRE = 32 / NS;            // V rows (float4) per thread per 32-key block
     const int warp = tid >> 5, lane = tid & 31;
-    const int ks = tid / DV, d = (tid % DV) * 4;
     const int nk = j1 - j0;
+    const int nb = (nk + 31) >> 5;
     const int jn = S - 1 - j0;  // relative index of the position being decoded (inside this item iff 0 <= jn < nk)
+    const bool mine = jn >= 0 && jn < nk && ((jn & 31) >> 2) == warp;  // this warp owns the new position
+    const int bn = jn >> 5;
     const float sqrt_hd = sqrtf((float)HD);
 
-    auto load_k_row = [&](int jr, float* dst) {  // cache row of relative key jr (zeros outside the range / for the new key)
+    auto load_row = [&](const float* base, int jr, float* dst) {  // cache row of relative key jr (zeros outside / new key)
         if (jr < nk && jr != jn) {
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) ld_vec<VEC>(Kc + (size_t)(j0 + jr) * HD + (c * 32 + lane) * VEC, dst + c * VEC);
+            for (int c = 0; c < NCH; ++c) ld_vec<VEC>(base + (size_t)(j0 + jr) * HD + (c * 32 + lane) * VEC, dst + c * VEC);
         } else {
 #pragma unroll
             for (int i = 0; i < DPL; ++i) dst[i] = 0.0f;
         }
     };
-    auto load_v = [&](int jr) -> float4 {
-        return (jr < nk && jr != jn) ? ldcg4(Vc + (size_t)(j0 + jr) * HD + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-
-    // ---- prefetch block 0 from the cache (independent of this step's q) ----
-    float kr[ATT_ROWS][DPL];
-    float4 vr[VPRE];
+    // ---- batch 0 from the cache (independent of this step's q) ----
+    float kr[ATT_ROWS][DPL], vr[ATT_ROWS][DPL];
 #pragma unroll
-    for (int u = 0; u < ATT_ROWS; ++u) load_k_row(warp + MEGA_WARPS * u, kr[u]);
+    for (int u = 0; u < ATT_ROWS; ++u) load_row(Kc, warp * ATT_ROWS + u, kr[u]);
 #pragma unroll
-    for (int i = 0; i < VPRE; ++i) vr[i] = load_v(ks + NS * i);
-    if constexpr (DBG) ck[1] = clock64();
-    // no counter wait here: only the <= H * 8 attention CTAs read xq, so they poll the tagged words directly (one L2
-    // round trip less than counter-then-data; the all-CTA hops keep the counter because 148 x 256 pollers contend)
-    (void)cnt_in;
-    (void)target_in;
-    if constexpr (DBG) ck[2] = clock64();
-    // ---- this step's q, and k / v of the position being decoded: every tagged load in flight at once ----
-    float qr[DPL], knew[DPL];
-    float4 vnew = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool v_mine = jn >= 0 && jn < nk && (jn % NS) == ks;          // this thread's key slice contains the new position
-    const bool k_mine = jn >= 0 && jn < nk && (jn % MEGA_WARPS) == warp;  // this warp scores the new position
+    for (int u = 0; u < ATT_ROWS; ++u) load_row(Vc, warp * ATT_ROWS + u, vr[u]);
+    if constexpr (DBG) ck[1] = ck[2] = ck[7] = clock64();
+    // ---- this step's q (and k / v of the position being decoded) ----
+    float qr[DPL], knew[DPL], vnew[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) knew[i] = vnew[i] = 0.0f;
     {
-        constexpr int NW16 = (DPL + 1) / 2;  // 16-byte words ({v, tag, v, tag}) per lane for HD floats ... 8-byte for DPL == 1
         const float* qp = xq + 2 * (size_t)(h * HD);
         const float* kp = xq + 2 * (size_t)(D + h * HD);
-        const float* vp = xq + 2 * (size_t)(2 * D + h * HD + d);  // 4 consecutive elements: two 16-byte words
+        const float* vp = xq + 2 * (size_t)(2 * D + h * HD);
         uint32_t spins = 0;
         bool ok = false;
         while (!ok) {
-            ok = true;
-            if constexpr (DPL == 1) {
-                const uint2 a = ld_x8(qp + 2 * lane);
-                ok = ((a.y ^ tag_in) & tmask) == 0u;
-                qr[0] = __uint_as_float(a.x);
-                if (k_mine) {
-                    const uint2 b = ld_x8(kp + 2 * lane);
-                    ok = ok && ((b.y ^ tag_in) & tmask) == 0u;
-                    knew[0] = __uint_as_float(b.x);
-                }
-            } else {
-                uint4 a[NW16], b[NW16];
-#pragma unroll
-                for (int c = 0; c < NCH; ++c)
-#pragma unroll
-                    for (int w2 = 0; w2 < VEC / 2; ++w2) {
-                        const int e = (c * 32 + lane) * VEC + 2 * w2;  // first of two consecutive elements
-                        a[c * (VEC / 2) + w2] = ld_x16(qp + 2 * e);
-                        if (k_mine) b[c * (VEC / 2) + w2] = ld_x16(kp + 2 * e);
-                    }
-#pragma unroll
-                for (int w2 = 0; w2 < NW16; ++w2) {
-                    ok = ok && tags_ok(a[w2], tag_in, tmask);
-                    qr[2 * w2] = __uint_as_float(a[w2].x);
-                    qr[2 * w2 + 1] = __uint_as_float(a[w2].z);
-                    if (k_mine) {
-                        ok = ok && tags_ok(b[w2], tag_in, tmask);
-                        knew[2 * w2] = __uint_as_float(b[w2].x);
-                        knew[2 * w2 + 1] = __uint_as_float(b[w2].z);
-                    }
-                }
+            ok = ld_tagged_lane<VEC, NCH>(qp, lane, tag_in, tmask, qr);
+            if (mine) {
+                const bool ok_k = ld_tagged_lane<VEC, NCH>(kp, lane, tag_in, tmask, knew);
+                const bool ok_v = ld_tagged_lane<VEC, NCH>(vp, lane, tag_in, tmask, vnew);
+                ok = ok && ok_k && ok_v;
             }
-            if (v_mine) {
-                const uint4 v0 = ld_x16(vp), v1 = ld_x16(vp + 4);
-                ok = ok && tags_ok(v0, tag_in, tmask) && tags_ok(v1, tag_in, tmask);
-                vnew = make_float4(__uint_as_float(v0.x), __uint_as_float(v0.z), __uint_as_float(v1.x), __uint_as_float(v1.z));
-            }
+            ok = __all_sync(0xffffffffu, ok);
             if (++spins > MEGA_SPIN_LIMIT) __trap();
         }
     }
     if constexpr (DBG) ck[3] = clock64() + (long long)(qr[0] == 123.f);
-    if (v_mine) __stcg(reinterpret_cast<float4*>(Vc + (size_t)(S - 1) * HD + d), vnew);
-    if (k_mine) {
+    if (mine) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) st_vec<VEC>(Kc + (size_t)(S - 1) * HD + (c * 32 + lane) * VEC, knew + c * VEC);
+        for (int c = 0; c < NCH; ++c) {
+            st_vec<VEC>(Kc + (size_t)(S - 1) * HD + (c * 32 + lane) * VEC, knew + c * VEC);
+            st_vec<VEC>(Vc + (size_t)(S - 1) * HD + (c * 32 + lane) * VEC, vnew + c * VEC);
+        }
     }
-    // ---- scores ----
-    for (int b = 0; b * 32 < nk; ++b) {
-        if (b > 0) {
+    // ---- batches: scores, online softmax, PV (per warp) ----
+    float m = -INFINITY, lsum = 0.0f, o[DPL];
 #pragma unroll
-            for (int u = 0; u < ATT_ROWS; ++u) load_k_row(b * 32 + warp + MEGA_WARPS * u, kr[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < ATT_ROWS; ++u) {
-            if (b * 32 + warp + MEGA_WARPS * u == jn && k_mine) {
-#pragma unroll
-                for (int i = 0; i < DPL; ++i) kr[u][i] = knew[i];
-            }
-        }
-        float s[ATT_ROWS];
+    for (int i = 0; i < DPL; ++i) o[i] = 0.0f;
+    for (int b = 0; b < nb; ++b) {
+        const int r0 = b * 32 + warp * ATT_ROWS;
+        const bool with_new = mine && b == bn;  // warp-uniform
+        float sc[ATT_ROWS + 1];
 #pragma unroll
         for (int u = 0; u < ATT_ROWS; ++u) {
             float a = 0.0f;
 #pragma unroll
             for (int i = 0; i < DPL; ++i) a = fmaf(qr[i], kr[u][i], a);
-            s[u] = a;
+            sc[u] = a;
+        }
+        {
+            float a = 0.0f;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) a = fmaf(qr[i], knew[i], a);
+            sc[ATT_ROWS] = a;
+        }
+        if (b + 1 < nb) {  // K registers are free: request the next batch
+#pragma unroll
+            for (int u = 0; u < ATT_ROWS; ++u) load_row(Kc, r0 + 32 + u, kr[u]);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int x = 16; x > 0; x >>= 1) {
 #pragma unroll
-            for (int u = 0; u < ATT_ROWS; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+            for (int u = 0; u <= ATT_ROWS; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], x);
         }
-        if (lane == 0) {
-#pragma unroll
-            for (int u = 0; u < ATT_ROWS; ++u) sc[b * 32 + warp + MEGA_WARPS * u] = s[u] / sqrt_hd;
+        if constexpr (DBG) {
+            if (b == 0) ck[7] = clock64() + (long long)(sc[0] == 123.f) + (long long)(sc[3] == 123.f);
         }
-    }
-    bar_sync(1, MEGA_CONSUMERS);
-    if constexpr (DBG) ck[4] = clock64();
-    // ---- softmax weights (every warp, all keys) ----
-    float pv[ATT_MAX_BLOCKS];
-    float M = -INFINITY;
+        float mb = -INFINITY;
 #pragma unroll
-    for (int b = 0; b < ATT_MAX_BLOCKS; ++b) {
-        pv[b] = -INFINITY;
-        if (b * 32 < nk) {
-            if (b * 32 + lane < nk) pv[b] = sc[b * 32 + lane];
-            M = fmaxf(M, pv[b]);
+        for (int u = 0; u <= ATT_ROWS; ++u) {
+            const bool valid = u < ATT_ROWS ? (r0 + u < nk && r0 + u != jn) : with_new;
+            // s / sqrt(hd): for hd = 64, 256 the divisor is a power of two and the product with its reciprocal is the same
+            const float sv = (HD == 64 || HD == 256) ? sc[u] * (1.0f / sqrt_hd) : sc[u] / sqrt_hd;
+            sc[u] = valid ? sv : -INFINITY;
+            mb = fmaxf(mb, sc[u]);
         }
-    }
-    M = warp_max(M);
-    float Lsum = 0.0f;
+        if (mb > -INFINITY) {  // warp-uniform
+            const float mn = fmaxf(m, mb);
+            const float c = expf(m - mn);  // first batch: exp(-inf) = 0
+            float pj[ATT_ROWS + 1];
+            lsum *= c;
 #pragma unroll
-    for (int b = 0; b < ATT_MAX_BLOCKS; ++b) {
-        if (b * 32 < nk) {
-            pv[b] = expf(pv[b] - M);  // outside the range: exp(-inf) = 0
-            Lsum += pv[b];
-        } else {
-            pv[b] = 0.0f;
-        }
-    }
-    Lsum = warp_sum(Lsum);
-    if constexpr (DBG) ck[5] = clock64() + (long long)(Lsum == 123.f);
-    // ---- PV ----
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int b = 0; b < ATT_MAX_BLOCKS; ++b) {
-        if (b * 32 < nk) {  // uniform
-            if (b > 0) {
-#pragma unroll
-                for (int i = 0; i < VPRE; ++i) vr[i] = load_v(b * 32 + ks + NS * i);
+            for (int u = 0; u <= ATT_ROWS; ++u) {
+                pj[u] = expf(sc[u] - mn);  // rows outside the range: exp(-inf) = 0
+                lsum += pj[u];
             }
 #pragma unroll
-            for (int i = 0; i < VPRE; ++i) {
-                const int jr = b * 32 + ks + NS * i;
-                const float pj = __shfl_sync(0xffffffffu, pv[b], (ks + NS * i) & 31);
-                const float4 vj = (jr == jn) ? vnew : vr[i];
-                o.x = fmaf(pj, vj.x, o.x);
-                o.y = fmaf(pj, vj.y, o.y);
-                o.z = fmaf(pj, vj.z, o.z);
-                o.w = fmaf(pj, vj.w, o.w);
+            for (int i = 0; i < DPL; ++i) {
+                float a = o[i] * c;
+#pragma unroll
+                for (int u = 0; u < ATT_ROWS; ++u) a = fmaf(pj[u], vr[u][i], a);
+                o[i] = fmaf(pj[ATT_ROWS], vnew[i], a);  // p = 0 unless this warp holds the new position in this batch
             }
+            m = mn;
+        }
+        if constexpr (DBG) {
+            if (b == 0) ck[2] = clock64() + (long long)(lsum == 123.f);
+        }
+        if (b + 1 < nb) {
+#pragma unroll
+            for (int u = 0; u < ATT_ROWS; ++u) load_row(Vc, r0 + 32 + u, vr[u]);
         }
     }
-    *reinterpret_cast<float4*>(opart + ks * HD + d) = o;
-    bar_sync(1, MEGA_CONSUMERS);
-    float os = 0.0f;
-    if (tid < HD) {
-#pragma unroll
-        for (int q = 0; q < NS; ++q) os += opart[q * HD + tid];
+    if constexpr (DBG) ck[4] = clock64() + (long long)(lsum == 123.f);
+    // ---- merge the 8 per-warp partials ----
+    if (lane == 0) {
+        wml[2 * warp] = m;
+        wml[2 * warp + 1] = lsum;
     }
-    if constexpr (DBG) ck[6] = clock64() + (long long)(os == 123.f);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        float* dst = wpart + warp * HD + (c * 32 + lane) * VEC;
+        if constexpr (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
+        else if constexpr (VEC == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+        else *dst = o[0];
+    }
+    bar_sync(1, MEGA_CONSUMERS);
+    if constexpr (DBG) ck[5] = clock64();
     if (tid < HD) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < MEGA_WARPS; ++w) M = fmaxf(M, wml[2 * w]);
+        float Lsum = 0.0f, os = 0.0f;
+#pragma unroll
+        for (int w = 0; w < MEGA_WARPS; ++w) {
+            const float cw = expf(wml[2 * w] - M);  // warps without keys: exp(-inf) = 0
+            Lsum = fmaf(wml[2 * w + 1], cw, Lsum);
+            os = fmaf(wpart[w * HD + tid], cw, os);
+        }
         st_tagged(o_out, item * HD + tid, os, tag_out);
         if (tid == 0) st_tagged2(ml_out, item * 2, M, Lsum, tag_out);
     }
     if constexpr (DBG) {
+      ck[6] = clock64();
       if (dbg != nullptr && tid == 0) {
-#pragma unroll
-        for (int q = 0; q < 6; ++q) dbg[q] = (unsigned long long)(ck[q + 1] - ck[q]);
+        // [prefetch issue, poll until q seen, dots + shuffles of batch 0, softmax weights + PV, later batches, barrier + merge + store]
+        dbg[0] = (unsigned long long)(ck[1] - ck[0]);
+        dbg[1] = (unsigned long long)(ck[3] - ck[1]);
+        dbg[2] = (unsigned long long)(ck[7] - ck[3]);
+        dbg[3] = (unsigned long long)(ck[2] - ck[7]);
+        dbg[4] = (unsigned long long)(ck[4] - ck[2]);
+        dbg[5] = (unsigned long long)(ck[6] - ck[4]);
       }
     }
 }
@@ -862,8 +858,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     // scratch region: sampling sort keys | attention scores + PV partials | mlp.c_proj group partials |
     // partial-sum gather (never live together)
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + off);
-    float* att_sc = reinterpret_cast<float*>(smem_raw + off);            // [160]
-    float* att_op = reinterpret_cast<float*>(smem_raw + off + 1024);     // [1024]
+    float* att_sc = reinterpret_cast<float*>(smem_raw + off);            // [8][2] per-warp (max, sum)
+    float* att_op = reinterpret_cast<float*>(smem_raw + off + 1024);     // [8][hd] per-warp PV partials
     float* part = reinterpret_cast<float*>(smem_raw + off);              // [2][D]
     float* gat = reinterpret_cast<float*>(smem_raw + off);               // [G][8]
     off += MEGA_SCRATCH_BYTES;
@@ -1059,7 +1055,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     float* vh = vc + (size_t)h * p.S_max * HD;
 #define GV_ATT_CASE(hd)                                                                                                     \
     case hd:                                                                                                                \
-        att_item<hd, TRACE>(kh, vh, p.xq, D, h, j0, j1, S, tg + TG_XQ, hc + HC_XQ * GV_HOP_STRIDE, 0u, att_sc, att_op, tid,      \
+        att_item<hd, TRACE>(kh, vh, p.xq, D, h, j0, j1, S, tg + TG_XQ, att_sc, att_op, tid,                                       \
                      p.att_o, p.att_ml, cta, tg + TG_AO, tmask, (TRACE && tr && ts + 20 <= p.trace_slots) ? trow + ts + 14 : nullptr); \
         break;
                     switch (HD) {

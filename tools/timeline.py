@@ -123,7 +123,7 @@ def main():
         for name, a in v["segments"].items():
             print(f"  {name:20s} med {a['med']/1e3:6.2f} us  max {a['max']/1e3:6.2f}  critical-path {a['crit']/1e3:6.2f}")
         print("  head:", {n: round(x / 1e3, 2) for n, x in v["head"].items()})
-        print("  attention item cycles (prefetch issue, XQ hop wait, tagged loads, scores+barrier, softmax, PV+merge):", [int(x) for x in v["att_cycles"]])
+        print("  attention item cycles (prefetch issue, poll until q seen, dots+shuffles, softmax weights+PV, later batches, barrier+merge+store):", [int(x) for x in v["att_cycles"]])
         print("  weight wait per layer (thread 0):", {n: int(x) for n, x in v["weight_wait_ns"].items()}, "cycles")
 
 
