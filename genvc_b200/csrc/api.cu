@@ -66,7 +66,7 @@ struct genvc_ctx {
     // debug timeline of the fused decode kernel (genvc_debug_trace)
     unsigned long long* trace = nullptr;
     int trace_slots = 0, trace_step = 0;
-    int window = 3, dbg_nosync = 0, l2_ahead = 0, hop_settle = 0, hop_hold = 0;
+    int window = 3, dbg_nosync = 0, l2_ahead = 0, hop_settle = 0, hop_hold = 0, hop_near = -1, hop_near_ao = -1;
 
     // host mirror of the generation state
     int B = 0, P = 0;
@@ -354,7 +354,12 @@ int genvc_debug_tune(genvc_ctx* ctx, int window, int nosync, int l2_ahead_tiles,
     if (window > 0) ctx->window = std::min(window, (int)GV_MEGA_NSLOT);
     if (l2_ahead_tiles >= 0) ctx->l2_ahead = l2_ahead_tiles;
     if (hop_settle_ns >= 0) ctx->hop_settle = hop_settle_ns;
-    if (hop_hold >= 0) ctx->hop_hold = hop_hold;
+    if (hop_hold >= 1000) {  // 1000 + near + 100 * near_ao: explicit early-release margins (1000 = none)
+        ctx->hop_near = (hop_hold - 1000) % 100;
+        ctx->hop_near_ao = (hop_hold - 1000) / 100;
+    } else if (hop_hold >= 0) {
+        ctx->hop_hold = hop_hold;
+    }
     ctx->dbg_nosync = nosync ? 1 : 0;
     return GENVC_OK;
 }
@@ -634,7 +639,7 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         p.ids_out = reinterpret_cast<long long*>(ids_out_dev); p.latents_out = latents_out_dev; p.logits_out = logits_out_dev;
         p.status = status_dev;
         p.trace = ctx->trace; p.trace_slots = ctx->trace_slots; p.trace_step = ctx->trace_step;
-        p.window = ctx->window; p.dbg_nosync = ctx->dbg_nosync; p.l2_ahead_tiles = ctx->l2_ahead; p.hop_settle_ns = ctx->hop_settle; p.hop_hold = ctx->hop_hold;
+        p.window = ctx->window; p.dbg_nosync = ctx->dbg_nosync; p.l2_ahead_tiles = ctx->l2_ahead; p.hop_settle_ns = ctx->hop_settle; p.hop_hold = ctx->hop_hold; p.hop_near = ctx->hop_near; p.hop_near_ao = ctx->hop_near_ao;
         CK(launch_decode_mega(p, ctx->grid, st));
         ctx->nlaunch += 1;
         ctx->n_host = std::min(max_total, ctx->n_host + n_steps);

@@ -60,6 +60,7 @@ struct MegaParams {
     // tuning / debug knobs (genvc_debug_tune)
     int window;      // producer: max tiles in flight (1..GV_MEGA_NSLOT)
     int l2_ahead_tiles;  // producer: L2 prefetch distance in tiles (0 = off)
+    int hop_near, hop_near_ao;  // early-release margins of the hops (-1 = default; decode_mega.cu: hop_wait)
     int hop_hold;        // 1: the producer issues no new bulk copies while the consumers poll / load a hop
     int hop_settle_ns;   // pause between seeing a hop counter complete and loading the data (decode_mega.cu: hop_wait)
     int dbg_nosync;  // consumers do not wait for exchange data (results are garbage; streaming-rate probe)

@@ -192,7 +192,9 @@ int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, in
  *   l2_ahead_tiles >= 0: distance (in 16 KB tiles per SM) at which the producer prefetches the
  *                weight stream HBM -> L2 ahead of the shared-memory ring (0 = off; < 0 keeps);
  *   hop_settle_ns >= 0: pause between seeing an exchange counter complete and loading the data (< 0 keeps);
- *   hop_hold >= 0: 1 = the producer issues no new bulk copies while the consumers poll / load an exchange. */
+ *   hop_hold 0 / 1: 1 = the producer issues no new bulk copies while the consumers poll / load an exchange;
+ *   hop_hold >= 1000: 1000 + near + 100 * near_ao = early-release margins of the exchanges (how many arrivals may be
+ *   outstanding when a CTA starts polling the tagged data itself; 1000 = none; default: grid / 37 and items / 3 <= 4). */
 int genvc_debug_tune(genvc_ctx* ctx, int window, int nosync, int l2_ahead_tiles, int hop_settle_ns, int hop_hold);
 
 #ifdef __cplusplus
