@@ -264,9 +264,10 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
 __device__ __forceinline__ void red_relaxed_add(unsigned* p, unsigned v) {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// every consumer thread's exchange stores are issued (program order before the barrier), then one arrival
+// One arrival per CTA, by thread 0 as soon as ITS warp's exchange stores are issued: the counter is only a hint (the
+// tags validate the data), so it may run ahead of the other warps' stores by their skew -- no block barrier here.
+// Every hop_arrive is followed by a hop_wait (with its barrier) before shared memory is reused.
 __device__ __forceinline__ void hop_arrive(unsigned* cnt, int tid) {
-    bar_sync(1, MEGA_CONSUMERS);
     if (tid == 0) red_relaxed_add(cnt, 1u);
 }
 // `near`: the CTA is released when all but `near` arrivals are in; its threads then spin on the tagged words themselves
