@@ -66,7 +66,7 @@ struct genvc_ctx {
     // debug timeline of the fused decode kernel (genvc_debug_trace)
     unsigned long long* trace = nullptr;
     int trace_slots = 0, trace_step = 0;
-    int window = 3, dbg_nosync = 0, l2_ahead = 0, hop_settle = 0, hop_hold = 0, hop_near = -1, hop_near_ao = -1;
+    int window = 2, dbg_nosync = 0, l2_ahead = 0, hop_settle = 0, hop_hold = 0, hop_near = -1, hop_near_ao = -1;
 
     // host mirror of the generation state
     int B = 0, P = 0;
@@ -194,7 +194,8 @@ int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
     const int nxv = g.d_model / 128;
     ctx->mega_ok = (nxv == 1 || nxv == 2 || nxv == 4 || nxv == 8) && ceil_div(4 * g.d_model, ctx->grid) <= 32 &&
                    ceil_div(g.n_audio_vocab, ctx->grid) <= 32 && g.n_audio_vocab <= 2048 && g.n_head * 8 <= ctx->grid &&
-                   g.d_model / 8 <= ctx->grid && ctx->grid <= 512 &&
+                   g.d_model / 8 <= ctx->grid && ctx->grid <= 304 &&
+                   mega_smem_bytes(g.d_model, (g.n_audio_vocab + 15) / 16 * 16) <= 232448 &&
                    (uint64_t)g.max_gen_mel_tokens * ((uint64_t)GV_TAGS_PER_LAYER * g.n_layer + 1ull) < 0x7FFFFFFFull;
     plan_workspace(ctx);
     *out = ctx;

@@ -46,7 +46,15 @@ namespace gv {
 #define MEGA_SPIN_LIMIT (1u << 26)
 #define NSLOT GV_MEGA_NSLOT
 #define UPT GV_MEGA_UPT
-#define MEGA_SCRATCH_BYTES (16384 + 512)
+// scratch region (never live together): attention per-warp (max, sum) + PV partials (1 KB + 8 * hd floats <= 9 KB) |
+// mlp.c_proj group partials [2][D] floats | partial-sum gather [G][8] floats | sampling sort keys [GV_SORT_N] u64 = 16 KB.
+// The sort keys run over into the two residual vectors that follow the scratch region (dead while a token is sampled),
+// which is what makes room for a twelfth ring slot.
+__host__ __device__ inline size_t mega_scratch_bytes(int D) {
+    const size_t spill = 2 * (size_t)D * sizeof(float);                    // xres0 + xres1
+    const size_t need = (size_t)GV_SORT_N * 8 > spill ? (size_t)GV_SORT_N * 8 - spill : 0;
+    return need > 9728 ? need : 9728;
+}
 
 enum { TG_XQ = 0, TG_AO = 1, TG_X1 = 2, TG_PP = 3, TG_X2 = 4 };
 
@@ -867,15 +875,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     float* att_op = reinterpret_cast<float*>(smem_raw + off + 1024);     // [8][hd] per-warp PV partials
     float* part = reinterpret_cast<float*>(smem_raw + off);              // [2][D]
     float* gat = reinterpret_cast<float*>(smem_raw + off);               // [G][8]
-    off += MEGA_SCRATCH_BYTES;
-    float* slog = reinterpret_cast<float*>(smem_raw + off);  // [Vpad] logits of the step being sampled
-    off += (size_t)p.Vpad * sizeof(float);
+    off += mega_scratch_bytes(D);
     float* xres0 = reinterpret_cast<float*>(smem_raw + off);  // [D] residual stream entering the block (= QKV GEMV input)
     off += (size_t)D * sizeof(float);
     float* xres1 = reinterpret_cast<float*>(smem_raw + off);  // [D] residual stream after attention (= FC GEMV input)
     off += (size_t)D * sizeof(float);
     float* xo = reinterpret_cast<float*>(smem_raw + off);  // [D] attention output (PROJ input) / latent (head input)
     off += (size_t)D * sizeof(float);
+    float* slog = reinterpret_cast<float*>(smem_raw + off);  // [Vpad] logits of the step being sampled
+    off += (size_t)p.Vpad * sizeof(float);
     ring.full = reinterpret_cast<uint64_t*>(smem_raw + off);
     off += 16 * sizeof(uint64_t);
     ring.empty = reinterpret_cast<uint64_t*>(smem_raw + off);
@@ -1352,7 +1360,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
 size_t mega_smem_bytes(int D, int Vpad) {
     size_t off = (size_t)NSLOT * slot_floats(D) * sizeof(float);
     off = (off + 127) & ~size_t(127);
-    off += MEGA_SCRATCH_BYTES;
+    off += mega_scratch_bytes(D);
     off += (size_t)Vpad * sizeof(float) + 3 * (size_t)D * sizeof(float);
     off += 32 * sizeof(uint64_t);
     off += (32 + 64 + 16) * sizeof(float) + 16 * sizeof(int) + 8 * sizeof(int);
@@ -1377,7 +1385,7 @@ static cudaError_t launch_nxv(const MegaParams& p, int grid, size_t smem, cudaSt
 cudaError_t launch_decode_mega(const MegaParams& p, int grid, cudaStream_t st) {
     const int hd = p.D / p.H;
     if (p.D % 128 || p.D > 1024 || !(hd == 32 || hd == 64 || hd == 128 || hd == 256)) return cudaErrorInvalidValue;
-    if ((size_t)grid * 8 * sizeof(float) > 16384 || p.H * 8 > grid) return cudaErrorInvalidValue;
+    if ((size_t)grid * 8 * sizeof(float) > 9728 || p.H * 8 > grid) return cudaErrorInvalidValue;
     const size_t smem = mega_smem_bytes(p.D, p.Vpad);
     switch (p.D / 128) {
         case 1: return launch_nxv<1>(p, grid, smem, st);

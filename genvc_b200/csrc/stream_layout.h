@@ -37,7 +37,7 @@ struct StreamDims {
 };
 
 // shared-memory ring of the fused kernel: GV_MEGA_NSLOT slots of GV_MEGA_UPT units each
-#define GV_MEGA_NSLOT 11
+#define GV_MEGA_NSLOT 12
 #define GV_MEGA_UPT 4
 
 GV_HD int unit_floats(int D) { return D + 4; }
