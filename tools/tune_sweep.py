@@ -20,8 +20,9 @@ kw = dict(do_sample=True, top_p=0.85, top_k=1, temperature=0.85, repetition_pena
 settles = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "0,50,100,200,400".split(","))]
 windows = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "4".split(","))]
 holds = [int(x) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else "0".split(","))]
-for w, sset, hh in itertools.product(windows, settles, holds):
-    eng.tune(window=w, hop_settle_ns=sset, hop_hold=hh)
+aheads = [int(x) for x in (sys.argv[4].split(",") if len(sys.argv) > 4 else "-1".split(","))]
+for w, sset, hh, ah in itertools.product(windows, settles, holds, aheads):
+    eng.tune(window=w, hop_settle_ns=sset, hop_hold=hh, l2_ahead=ah)
     best = 1e9
     for rep in range(4):
         eng.timing = []
@@ -31,4 +32,4 @@ for w, sset, hh in itertools.product(windows, settles, holds):
         torch.cuda.synchronize()
         t = sum(a.elapsed_time(b) for a, b, _, _ in eng.timing) / sum(n for _, _, n, _ in eng.timing)
         best = min(best, t)
-    print(f"window {w} settle {sset:4d} ns hold {hh}: {best:.4f} ms/token", flush=True)
+    print(f"window {w} settle {sset:4d} ns hold {hh} ahead {ah}: {best:.4f} ms/token", flush=True)
