@@ -766,7 +766,6 @@ struct Producer {
     uint32_t t = 0, slot = 0, phase = 0;
     uint32_t land = 0;  // tiles [0, land) have been seen complete (published to the consumers through ring.landed)
     uint32_t window;    // at most this many tiles requested but not landed
-    uint32_t window_base = 0, window_qkv = 0;  // per-phase windows (QKV / PROJ tiles refill right after the long hop stretch)
     volatile int* stop;
     volatile int* hold = nullptr;  // non-null: do not issue new copies while *hold != 0 (consumers are polling / loading a hop)
     uint64_t policy;
@@ -842,10 +841,8 @@ __device__ bool produce_forward(Producer& pr, const MegaParams& p, const StreamD
     for (int ph = 0; ph < 5; ++ph) nun[ph] = ph_units(sd, ph, cta);
     for (int l = 0; l < p.L; ++l) {
         const float* lw = base + (long long)l * lfl;
-        for (int ph = PH_QKV; ph <= PH_P2; ++ph) {
-            pr.window = (ph <= PH_PROJ && pr.window_qkv) ? pr.window_qkv : pr.window_base;
+        for (int ph = PH_QKV; ph <= PH_P2; ++ph)
             if (!pr.issue_units(lw, nun[ph], uf)) return false;
-        }
     }
     if (!pr.issue(p.blob + p.lnf_off, 4 * D, false)) return false;  // ln_f and final_norm parameters
     const float* hw = base + (long long)p.L * lfl;
@@ -936,13 +933,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
             if (p.hop_hold) pr.hold = hold;
             pr.region = p.stream + cta_base(sd, cta);
             pr.region_floats = cta_base(sd, cta + 1) - cta_base(sd, cta);
-            pr.window_base = pr.window;
-            if (p.l2_ahead_tiles >= 100) {  // debug knob: values >= 100 = window of the QKV / PROJ tiles + 100
-                pr.window_qkv = (uint32_t)min(p.l2_ahead_tiles - 100, NSLOT);
-            } else {
-                pr.ahead_floats = min((long long)p.l2_ahead_tiles * slot_floats(D), pr.region_floats - slot_floats(D));
-                if (pr.ahead_floats < 0) pr.ahead_floats = 0;
-            }
+            pr.ahead_floats = min((long long)p.l2_ahead_tiles * slot_floats(D), pr.region_floats - slot_floats(D));
+            if (pr.ahead_floats < 0) pr.ahead_floats = 0;
             bool ok = true;
             for (int i = 0; i < p.n_steps && ok; ++i) {
                 if (i == 0 && had_pending) continue;
