@@ -206,6 +206,26 @@ def test_latent_pass(name, cuda_device):
     assert ok, f"latent-pass max err {err}"
 
 
+def test_full_size_batch_rows_equal_single_row_fused(cuda_device):
+    """BASELINE configs[2]/[3] shape at L=30, D=1024: a batch of 4 different utterances (equal T) through the batched
+    per-op path gives, row by row, the ids the fused single-row kernel gives for the same inputs (greedy)."""
+    fx = load_golden("full_h4_cfg1")
+    gen = torch.Generator().manual_seed(21)
+    B, T, n = 4, 25, 20
+    codes = torch.randint(0, 256, (B, T), generator=gen).to(cuda_device)
+    cond1 = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device)
+    kw = dict(do_sample=True, top_p=0.85, top_k=1, temperature=0.85, num_beams=1, length_penalty=1.0,
+              repetition_penalty=2.0, output_attentions=False, max_new_tokens=n)
+    g1 = make_gpt(fx, cuda_device)
+    single = [g1.generate(cond1, codes[b:b + 1], decode_mode=2, **kw)[0].cpu() for b in range(B)]
+    gB = make_gpt(fx, cuda_device, max_batch=B)
+    ids = gB.generate(cond1.expand(B, -1, -1).contiguous(), codes, **kw).cpu()
+    assert ids.shape[0] == B
+    for b in range(B):
+        m = min(ids.shape[1], single[b].shape[0])
+        assert torch.equal(ids[b, :m], single[b][:m]), f"row {b}: first mismatch at {(ids[b, :m] != single[b][:m]).nonzero()[:1].tolist()}"
+
+
 # ------------------------------------------------------------------------------------ streaming protocol
 @pytest.mark.parametrize("name,chunk", [("toy_d128_eos", 8), ("toy_d128_greedy", 5), ("toy_d128_topk20", 8)])
 def test_streaming_generator_protocol(name, chunk, cuda_device):
