@@ -183,10 +183,12 @@ def test_batched_rows_equal_reference(cuda_device):
     out = g.get_style_emb(fx["mel"].to(cuda_device))
     ok, err = close(out, fx["style_emb"], 2e-4, 1e-4)
     assert ok, err
-    ids, lats = _run_generate(fx, g, cuda_device, 0)
-    assert torch.equal(ids.cpu(), fx["ids"])
-    ok, err = close(lats[:, fx["steps"].to(lats.device)], fx["latents"], LAT_ATOL, LAT_RTOL)
-    assert ok, f"latent max err {err}"
+    for mode in (1, 0):  # batched per-op path, then the default (row by row through the fused kernel)
+        ids, lats = _run_generate(fx, g, cuda_device, mode)
+        assert torch.equal(ids.cpu(), fx["ids"]), f"mode {mode}"
+        if mode == 1:  # rows that finished keep producing (discarded) latents in the batched loop only
+            ok, err = close(lats[:, fx["steps"].to(lats.device)], fx["latents"], LAT_ATOL, LAT_RTOL)
+            assert ok, f"latent max err {err}"
 
 
 # ------------------------------------------------------------------------------------ latent pass
@@ -219,11 +221,13 @@ def test_full_size_batch_rows_equal_single_row_fused(cuda_device):
     g1 = make_gpt(fx, cuda_device)
     single = [g1.generate(cond1, codes[b:b + 1], decode_mode=2, **kw)[0].cpu() for b in range(B)]
     gB = make_gpt(fx, cuda_device, max_batch=B)
-    ids = gB.generate(cond1.expand(B, -1, -1).contiguous(), codes, **kw).cpu()
-    assert ids.shape[0] == B
-    for b in range(B):
-        m = min(ids.shape[1], single[b].shape[0])
-        assert torch.equal(ids[b, :m], single[b][:m]), f"row {b}: first mismatch at {(ids[b, :m] != single[b][:m]).nonzero()[:1].tolist()}"
+    for mode in (1, 0):  # 1: batched per-op kernels; 0: default (small batches go row by row through the fused kernel)
+        ids = gB.generate(cond1.expand(B, -1, -1).contiguous(), codes, decode_mode=mode, **kw).cpu()
+        assert ids.shape[0] == B
+        for b in range(B):
+            m = min(ids.shape[1], single[b].shape[0])
+            assert torch.equal(ids[b, :m], single[b][:m]), \
+                f"mode {mode} row {b}: first mismatch at {(ids[b, :m] != single[b][:m]).nonzero()[:1].tolist()}"
 
 
 # ------------------------------------------------------------------------------------ streaming protocol
