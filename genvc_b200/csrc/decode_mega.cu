@@ -10,26 +10,27 @@
 //   * one persistent CTA per SM (cooperative launch), each owning a fixed slice of every matrix;
 //     the slices are pre-packed so a CTA reads one contiguous byte stream (stream_layout.h);
 //   * a producer thread per CTA streams that region HBM -> shared memory with 1-D bulk TMA copies
-//     (cp.async.bulk, completion on mbarriers) into an 11 x 16 KB ring.  The weight stream does
+//     (cp.async.bulk, completion on mbarriers) into a 12 x 16 KB ring.  The weight stream does
 //     not depend on activations, so it runs ahead across phase boundaries and across tokens: HBM
 //     does not idle while the consumers exchange activations.  At most `window` tiles are in
 //     flight per SM (enough to cover the bandwidth-delay product, few enough not to queue in front
 //     of the latency-critical exchange traffic);
-//   * 16 consumer warps do the GEMVs out of shared memory in fp32 FMA.  K = D matrices (QKV, attn
+//   * 8 consumer warps (two warpgroups at 232 registers: the producer warpgroup hands its registers over with
+//     setmaxnreg) do the GEMVs out of shared memory in fp32 FMA.  K = D matrices (QKV, attn
 //     proj, FC, logits head): a unit is one output column, one warp per unit, the activation vector
 //     in 32 registers per lane, 8 LDS.128 + 32 FFMA per lane per unit and one shuffle tree — no
 //     cross-warp reduction.  mlp.c_proj (K = 4D) is split along K instead: the CTA that computed
-//     u_k owns ROW k of W_proj2 and accumulates u_k * W[k, :] into a D-wide partial (thread t owns
-//     outputs 2t, 2t+1: no reduction at all), so the 4D-wide activation never crosses CTAs; the G
+//     u_k owns ROW k of W_proj2 and accumulates u_k * W[k, :] into a D-wide partial (a thread owns
+//     eight outputs per warp group), so the 4D-wide activation never crosses CTAs; the G
 //     partials are summed in a fixed order by D/8 reducer CTAs (deterministic, no float atomics);
 //   * hops go through L2: producers store {value, tag} words (tag = global hop number) and bump an
-//     arrival counter (one relaxed red per CTA, no fence); ONE thread per CTA spins on the counter,
-//     a block barrier releases the others, which load the words they need and re-poll the rare word
-//     whose tag is stale.  The counter is only a hint — validity comes from the tags;
+//     arrival counter (one relaxed red per CTA, no fence, no barrier); ONE thread per CTA spins on the
+//     counter and releases the CTA when all but a few arrivals are in; the threads load the words they
+//     need and spin on those whose tag is stale.  The counter is only a hint — validity comes from the tags;
 //   * single-token attention is split over (head, key range) items run by the first H*nsplit CTAs:
-//     the item's K/V rows are requested from the cache BEFORE the hop wait, online softmax with
-//     warp-shuffle reductions, 16 warp states merged through shared memory; the item that covers
-//     the newest position takes k/v from the exchange buffer and appends them to the cache;
+//     the item's first K/V rows are requested from the cache BEFORE q is polled, online softmax per
+//     warp with warp-shuffle reductions, 8 warp states merged through shared memory; the item that
+//     covers the newest position takes k/v from the exchange buffer and appends them to the cache;
 //   * sampling is computed redundantly by every CTA (same data, same code => same token), so the
 //     next token needs no broadcast.
 // No tensor cores: at M = 1 there is no reuse to feed them; fp32 keeps greedy parity.
