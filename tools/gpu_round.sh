@@ -10,7 +10,7 @@ if [ -z "$SKIP_TESTS" ]; then
   tail -5 $OUT/pytest_gpu.log
 fi
 timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"; cat $OUT/bench.json
-timeout 300 python tools/timeline.py --window 4 --out $OUT/timeline.json > $OUT/timeline.txt 2>&1; cat $OUT/timeline.txt
+timeout 300 python tools/timeline.py --out $OUT/timeline.json > $OUT/timeline.txt 2>&1; cat $OUT/timeline.txt
 if [ -z "$SKIP_NCU" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1000 -c 700 --csv --log-file $OUT/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/ncu_launches.log 2>&1; echo "ncu list exit $?"
