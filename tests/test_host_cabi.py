@@ -178,3 +178,27 @@ def test_replicas_two_ranks_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True, True), (1, True, True)]
+
+
+@pytest.mark.parametrize("L,D,H", [(30, 1024, 4), (30, 1024, 16), (2, 128, 4), (2, 512, 2)])
+def test_decode_stream_and_cache_sizes_follow_the_layout(L, D, H):
+    """The decode weight stream holds every unit exactly once: per layer 3D + D + 4D + 4D units and V head units of
+    D + 4 floats (stream_layout.h); the KV cache is [L][2][max_batch][H][max_seq][hd].  Layout queries need no device."""
+    from genvc_b200.config import GenVCDims, make_config_dict
+    from genvc_b200.weights import c_config
+
+    lib = _lib()
+    dims = GenVCDims.from_config(make_config_dict(L, D, H))
+    cfg = c_config(dims)
+    ctx = C.c_void_p()
+    assert lib.genvc_create(C.byref(cfg), 0, C.byref(ctx)) == 0
+    try:
+        grid = lib.genvc_decode_grid(ctx)
+        assert grid >= 1
+        V = cfg.n_audio_vocab
+        expect = (L * 12 * D + V) * (D + 4)
+        assert lib.genvc_stream_floats(ctx) == expect
+        assert lib.genvc_kv_floats(ctx) == L * 2 * cfg.max_batch * cfg.max_seq * D
+        assert lib.genvc_workspace_bytes(ctx) > 0
+    finally:
+        lib.genvc_destroy(ctx)
