@@ -42,6 +42,9 @@ struct genvc_ctx {
     int n_sm = 0;
     int grid = 0;  // CTAs of the fused decode kernel
     bool mega_ok = false;
+    bool batch_ok = false;  // batched fused decode kernel (decode_batch.cu) supports this shape
+    int fused_rows = 1;     // rows the exchange buffers are sized for (1, or GV_BATCH_ROWS when max_batch > 1)
+    int gs_cur = 0;         // which copy of the (double-buffered) generation state is current
     Layout layout;
     StreamDims sdims;
     mutable std::string err;
@@ -54,7 +57,7 @@ struct genvc_ctx {
     char* ws = nullptr;
 
     // workspace offsets (bytes)
-    size_t o_state, o_seen, o_status_scratch, o_pend_logits, o_pend_latent, o_splitk, o_X, o_A, o_QKV, o_U;
+    size_t o_state, o_seen, state_stride = 0, seen_stride = 0, o_tokx, o_flags, o_status_scratch, o_pend_logits, o_pend_latent, o_splitk, o_X, o_A, o_QKV, o_U;
     // exchange buffers of the fused decode kernel ({value, tag} pairs; one contiguous region)
     size_t o_xchg, xchg_bytes, o_xq, o_matt_o, o_matt_ml, o_x1, o_pp, o_x2, o_lg, o_hops, o_acc;
     size_t acc_bytes = 0;
@@ -85,6 +88,8 @@ struct genvc_ctx {
     T* at(size_t off) const {
         return reinterpret_cast<T*>(ws + off);
     }
+    GenState* gstate(int which) const { return at<GenState>(o_state + (size_t)which * state_stride); }
+    unsigned char* gseen(int which) const { return at<unsigned char>(o_seen + (size_t)which * seen_stride); }
     const float* w(uint64_t off) const { return blob + off; }
 
     int fail(int code, const char* fmt, ...) const {
@@ -95,6 +100,19 @@ struct genvc_ctx {
         va_end(ap);
         err = buf;
         return code;
+    }
+};
+
+// current-device guard of the entry points: the library works on ctx->device and restores the caller's device
+struct DevGuard {
+    int prev = -1, dev;
+    cudaError_t err = cudaSuccess;
+    explicit DevGuard(int d) : dev(d) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DevGuard() {
+        if (prev >= 0 && prev != dev) (void)cudaSetDevice(prev);
     }
 };
 
@@ -113,20 +131,27 @@ static void plan_workspace(genvc_ctx* c) {
     const size_t D = g.d_model, V = g.n_audio_vocab, MB = g.max_batch, F = sizeof(float);
     c->Vpad = (int)((V + 15) / 16 * 16);
     Workspace w;
-    c->o_state = w.take(sizeof(GenState) + 64);
-    c->o_seen = w.take(MB * c->Vpad);
+    // generation state + repetition-penalty sets, two copies each: a fused launch reads one and writes the other
+    c->state_stride = (sizeof(GenState) + 64 + 255) / 256 * 256;
+    c->o_state = w.take(2 * c->state_stride);
+    c->seen_stride = (MB * c->Vpad + 255) / 256 * 256;
+    c->o_seen = w.take(2 * c->seen_stride);
     c->o_status_scratch = w.take(64);
+    c->o_flags = w.take(64);  // int[0]: an embedding kernel clamped an out-of-range id (decode path); int[1]: same, latent pass
     c->o_pend_logits = w.take(MB * V * F);
     c->o_pend_latent = w.take(MB * D * F);
     // exchange buffers of the fused decode kernel: {value, tag} pairs (2 floats per element)
-    const size_t items = (size_t)g.n_head * 8;  // att_nsplit() <= 8
-    c->o_xchg = c->o_xq = w.take(2 * 3 * D * F);
+    // (single-row kernel: H * att_nsplit() <= H * 8 items; batched kernel: rows * H * nsplit <= grid items)
+    const size_t FR = c->fused_rows = (MB > 1 && c->batch_ok) ? GV_BATCH_ROWS : 1;
+    const size_t items = std::max((size_t)g.n_head * 8, FR > 1 ? (size_t)c->grid : (size_t)0);
+    c->o_xchg = c->o_xq = w.take(2 * FR * 3 * D * F);
     c->o_matt_o = w.take(2 * items * (D / g.n_head) * F);
     c->o_matt_ml = w.take(2 * items * 2 * F);
-    c->o_x1 = w.take(2 * D * F);
-    c->o_pp = w.take(2 * (size_t)std::max(c->grid, 1) * D * F);
-    c->o_x2 = w.take(2 * D * F);
-    c->o_lg = w.take(2 * (size_t)c->Vpad * F);
+    c->o_x1 = w.take(2 * FR * D * F);
+    c->o_pp = w.take(2 * (size_t)std::max(c->grid, 1) * FR * D * F);
+    c->o_x2 = w.take(2 * FR * D * F);
+    c->o_lg = w.take(2 * FR * (size_t)c->Vpad * F);
+    c->o_tokx = w.take(2 * GV_BATCH_ROWS * F);
     c->o_hops = w.take(HC_COUNT * GV_HOP_STRIDE * sizeof(unsigned));
     c->acc_bytes = 2 * (size_t)g.n_layer * D * sizeof(unsigned long long);
     c->o_acc = w.take(c->acc_bytes);
@@ -197,6 +222,11 @@ int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
                    g.d_model / 8 <= ctx->grid && ctx->grid <= 304 &&
                    mega_smem_bytes(g.d_model, (g.n_audio_vocab + 15) / 16 * 16) <= 232448 &&
                    (uint64_t)g.max_gen_mel_tokens * ((uint64_t)GV_TAGS_PER_LAYER * g.n_layer + 1ull) < 0x7FFFFFFFull;
+    // batched fused kernel (decode_batch.cu): rows * H attention items must fit the grid (checked per call), the
+    // reducer CTAs (D / 8) and the 8-column residual stash per row must fit
+    ctx->batch_ok = ctx->mega_ok && ceil_div(g.d_model, ctx->grid) <= 8 &&
+                    batch_smem_bytes(g.d_model, (g.n_audio_vocab + 15) / 16 * 16) <= 232448 &&
+                    (uint64_t)g.max_gen_mel_tokens * ((uint64_t)GV_TAGS_PER_LAYER * g.n_layer + 1ull + GV_BATCH_TAGS_EXTRA) < 0x7FFFFFFFull;
     plan_workspace(ctx);
     *out = ctx;
     return GENVC_OK;
@@ -210,6 +240,12 @@ void genvc_destroy(genvc_ctx* ctx) {
 const char* genvc_last_error(const genvc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int genvc_decode_grid(const genvc_ctx* ctx) { return ctx ? ctx->grid : 0; }
+
+int genvc_fused_max_rows(const genvc_ctx* ctx) {
+    if (!ctx || !ctx->mega_ok) return 0;
+    if (!ctx->batch_ok || ctx->fused_rows <= 1) return 1;
+    return std::min({(int)GV_BATCH_ROWS, ctx->cfg.max_batch, ctx->grid / ctx->cfg.n_head});
+}
 
 uint64_t genvc_blob_floats(const genvc_ctx* ctx) { return ctx ? ctx->layout.total : 0; }
 int genvc_num_tensors(const genvc_ctx* ctx) { return ctx ? (int)ctx->layout.tensors.size() : 0; }
@@ -274,7 +310,8 @@ int genvc_pack_tc(genvc_ctx* ctx, float* tc_dev, uint64_t n_floats, void* stream
     if (!ctx->blob) return ctx->fail(GENVC_E_STATE, "bind weights first");
     if (!tc_dev || n_floats < genvc_tc_floats(ctx) || reinterpret_cast<uintptr_t>(tc_dev) % 128)
         return ctx->fail(GENVC_E_INVALID, "tensor-core weight buffer too small or misaligned");
-    CK(cudaSetDevice(ctx->device));
+    DevGuard guard(ctx->device);
+    CK(guard.err);
     uint64_t o = 0;
     for (const TcMat& m : tc_matrices(ctx)) {
         CK(gemm_tc_pack(ctx->w(m.off), m.N, m.K, m.ldw, m.w_nk, tc_dev + o, (cudaStream_t)stream));
@@ -307,7 +344,8 @@ int genvc_pack_stream(genvc_ctx* ctx, float* stream_dev, uint64_t n_floats, void
     if (!stream_dev || n_floats < genvc_stream_floats(ctx) || reinterpret_cast<uintptr_t>(stream_dev) % 128)
         return ctx->fail(GENVC_E_INVALID, "decode stream buffer too small or misaligned");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaSetDevice(ctx->device));
+    DevGuard guard(ctx->device);
+    CK(guard.err);
     const Layout& L = ctx->layout;
     for (int l = 0; l < ctx->cfg.n_layer; ++l) {
         const LayerOff& o = L.layers[l];
@@ -341,8 +379,10 @@ int genvc_bind_buffers(genvc_ctx* ctx, float* kv_dev, uint64_t kv_floats, void* 
     ctx->ws = static_cast<char*>(workspace_dev);
     ctx->prefilled = false;
     // exchange tags start at 1 over zeroed buffers
-    CK(cudaSetDevice(ctx->device));
+    DevGuard guard(ctx->device);
+    CK(guard.err);
     CK(cudaMemset(ctx->ws + ctx->o_xchg, 0, ctx->xchg_bytes));
+    CK(cudaMemset(ctx->ws + ctx->o_flags, 0, 64));
     CK(cudaDeviceSynchronize());
     ctx->tag_next = 1;
     return GENVC_OK;
@@ -383,8 +423,6 @@ static int check_ready(genvc_ctx* ctx) {
     if (!ctx) return GENVC_E_INVALID;
     if (!ctx->blob) return ctx->fail(GENVC_E_STATE, "weights not bound");
     if (!ctx->kv || !ctx->ws) return ctx->fail(GENVC_E_STATE, "buffers not bound");
-    cudaError_t e = cudaSetDevice(ctx->device);
-    if (e != cudaSuccess) return ctx->fail(GENVC_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     return GENVC_OK;
 }
 
@@ -479,6 +517,8 @@ extern "C" {
 // ---------------------------------------------------------------------------------------------
 int genvc_perceiver(genvc_ctx* ctx, const float* mel_dev, int B, int S_mel, float* latents_out_dev, void* stream) {
     if (int rc = check_ready(ctx)) return rc;
+    DevGuard guard(ctx->device);
+    CK(guard.err);
     const genvc_config& g = ctx->cfg;
     if (!mel_dev || !latents_out_dev) return ctx->fail(GENVC_E_INVALID, "null pointer");
     if (B <= 0 || B > g.max_batch) return ctx->fail(GENVC_E_INVALID, "batch %d outside [1, %d]", B, g.max_batch);
@@ -539,6 +579,8 @@ int genvc_perceiver(genvc_ctx* ctx, const float* mel_dev, int B, int S_mel, floa
 int genvc_embed_prefix(genvc_ctx* ctx, const float* cond_dev, const int64_t* text_ids_dev, int B, int T, float* prefix_out_dev,
                        void* stream) {
     if (int rc = check_ready(ctx)) return rc;
+    DevGuard guard(ctx->device);
+    CK(guard.err);
     const genvc_config& g = ctx->cfg;
     if (!cond_dev || !text_ids_dev || !prefix_out_dev) return ctx->fail(GENVC_E_INVALID, "null pointer");
     if (B <= 0 || T < 0 || T + 2 > g.n_text_pos)
@@ -547,12 +589,14 @@ int genvc_embed_prefix(genvc_ctx* ctx, const float* cond_dev, const int64_t* tex
     const int P = g.pc_latents + T + 2;
     CK(launch_embed_prefix(cond_dev, reinterpret_cast<const long long*>(text_ids_dev), B, T, g.pc_latents, g.d_model,
                            ctx->w(L.text_emb), ctx->w(L.text_pos), g.start_text, g.stop_text, prefix_out_dev, (long)P * g.d_model,
-                           (cudaStream_t)stream, &ctx->nlaunch));
+                           g.n_text_vocab, ctx->at<int>(ctx->o_flags), (cudaStream_t)stream, &ctx->nlaunch));
     return GENVC_OK;
 }
 
 int genvc_prefill(genvc_ctx* ctx, const float* prefix_dev, int B, int P, void* stream) {
     if (int rc = check_ready(ctx)) return rc;
+    DevGuard guard(ctx->device);
+    CK(guard.err);
     const genvc_config& g = ctx->cfg;
     if (!prefix_dev) return ctx->fail(GENVC_E_INVALID, "null pointer");
     if (B <= 0 || B > g.max_batch) return ctx->fail(GENVC_E_INVALID, "batch %d outside [1, %d]", B, g.max_batch);
@@ -566,11 +610,11 @@ int genvc_prefill(genvc_ctx* ctx, const float* prefix_dev, int B, int P, void* s
     // rows = [prefix (P) ; mel_embedding[start_audio] + mel_pos[0]]   (layers/gpt_inference.py:81-91)
     CK(launch_copy_rows(prefix_dev, (long)P * D, X, (long)M * D, B, (long)P * D, st, &ctx->nlaunch));
     CK(launch_embed_mel_rows(nullptr, B, 1, 0, g.start_audio, g.stop_audio, 0, D, ctx->w(L.mel_emb), ctx->w(L.mel_pos),
-                             X + (size_t)P * D, (long)M * D, st, &ctx->nlaunch));
+                             X + (size_t)P * D, (long)M * D, g.n_audio_vocab, ctx->at<int>(ctx->o_flags), st, &ctx->nlaunch));
     if (int rc = run_blocks(ctx, B, M, 0, nullptr, st)) return rc;
     if (int rc = run_head(ctx, B, M, P, nullptr, st)) return rc;
-    CK(launch_init_state(ctx->at<GenState>(ctx->o_state), ctx->at<unsigned char>(ctx->o_seen), B, P, g.n_audio_vocab, ctx->Vpad,
-                         g.start_audio, st, &ctx->nlaunch));
+    CK(launch_init_state(ctx->gstate(ctx->gs_cur), ctx->gseen(ctx->gs_cur), B, P, g.n_audio_vocab, ctx->Vpad, g.start_audio, st,
+                         &ctx->nlaunch));
     ctx->B = B;
     ctx->P = P;
     ctx->prefilled = true;
@@ -585,6 +629,8 @@ int genvc_prefill(genvc_ctx* ctx, const float* prefix_dev, int B, int P, void* s
 int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const float* exp_noise_dev, const int64_t* forced_ids_dev,
                  int64_t* ids_out_dev, float* latents_out_dev, float* logits_out_dev, int32_t* status_dev, int mode, void* stream) {
     if (int rc = check_ready(ctx)) return rc;
+    DevGuard guard(ctx->device);
+    CK(guard.err);
     if (!ctx->prefilled) return ctx->fail(GENVC_E_STATE, "genvc_decode before genvc_prefill");
     if (!sp || !ids_out_dev || !latents_out_dev || !status_dev) return ctx->fail(GENVC_E_INVALID, "null pointer");
     if (n_steps <= 0) return ctx->fail(GENVC_E_INVALID, "n_steps must be positive");
@@ -596,13 +642,17 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
     const int B = ctx->B, D = g.d_model, V = g.n_audio_vocab;
     int max_total = g.max_gen_mel_tokens;
     if (sp->max_new_tokens > 0) max_total = std::min(max_total, (int)sp->max_new_tokens);
-    const bool can_mega = ctx->mega_ok && ctx->stream_packed && B == 1 && ctx->n_sm == ctx->grid;
+    const bool fused_dev = ctx->stream_packed && ctx->n_sm == ctx->grid;
+    const bool can_batch = fused_dev && ctx->batch_ok && B > 1 && B <= GV_BATCH_ROWS && ctx->fused_rows >= B &&
+                           B * g.n_head <= ctx->grid;
+    const bool can_mega = (fused_dev && ctx->mega_ok && B == 1) || can_batch;
     if (mode == 2 && !can_mega)
-        return ctx->fail(GENVC_E_UNSUPPORTED, "fused decode needs batch 1, a packed decode stream and a supported shape");
+        return ctx->fail(GENVC_E_UNSUPPORTED, "fused decode needs batch <= %d (batch * heads <= %d), a packed decode stream and a "
+                         "supported shape", GV_BATCH_ROWS, ctx->grid);
     const bool mega = mode == 2 || (mode == 0 && can_mega);
-    GenState* gs = ctx->at<GenState>(ctx->o_state);
-    unsigned char* seen = ctx->at<unsigned char>(ctx->o_seen);
-    CK(cudaMemsetAsync(status_dev, 0, 2 * sizeof(int32_t), st));
+    GenState* gs = ctx->gstate(ctx->gs_cur);
+    unsigned char* seen = ctx->gseen(ctx->gs_cur);
+    CK(cudaMemsetAsync(status_dev, 0, 4 * sizeof(int32_t), st));
 
     if (mega) {
         const Layout& L = ctx->layout;
@@ -623,7 +673,7 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         p.acc = ctx->at<unsigned long long>(ctx->o_acc);
         CK(cudaMemsetAsync(p.acc, 0, ctx->acc_bytes, st));
         {   // exchange tags: unique per (launch, step, layer, buffer); restart over zeroed buffers before a wrap
-            const uint64_t need = (uint64_t)n_steps * ((uint64_t)GV_TAGS_PER_LAYER * g.n_layer + 1ull);
+            const uint64_t need = (uint64_t)n_steps * ((uint64_t)GV_TAGS_PER_LAYER * g.n_layer + 1ull + GV_BATCH_TAGS_EXTRA);
             if ((uint64_t)ctx->tag_next + need >= 0xFFFFFFF0ull) {
                 CK(cudaMemsetAsync(ctx->ws + ctx->o_xchg, 0, ctx->xchg_bytes, st));
                 ctx->tag_next = 1;
@@ -632,16 +682,21 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
             ctx->tag_next += (uint32_t)need;
         }
         p.pend_logits = ctx->at<float>(ctx->o_pend_logits); p.pend_latent = ctx->at<float>(ctx->o_pend_latent);
+        // the launch reads the current copy of the state and writes the other one
         p.st = gs; p.seen = seen;
+        p.st_out = ctx->gstate(ctx->gs_cur ^ 1); p.seen_out = ctx->gseen(ctx->gs_cur ^ 1);
+        p.B = B; p.tokx = ctx->at<float>(ctx->o_tokx);
         p.top_k = sp->top_k; p.top_p = sp->top_p; p.top_p_threshold = sp->top_p_threshold; p.temperature = sp->temperature;
         p.rep_penalty = sp->repetition_penalty; p.ignore_eos = sp->ignore_eos; p.stop_token = g.stop_audio;
         p.max_total = max_total; p.seed = sp->seed;
         p.noise = exp_noise_dev; p.forced = reinterpret_cast<const long long*>(forced_ids_dev);
         p.ids_out = reinterpret_cast<long long*>(ids_out_dev); p.latents_out = latents_out_dev; p.logits_out = logits_out_dev;
-        p.status = status_dev;
+        p.status = status_dev; p.bad_ids = ctx->at<int>(ctx->o_flags);
         p.trace = ctx->trace; p.trace_slots = ctx->trace_slots; p.trace_step = ctx->trace_step;
         p.window = ctx->window; p.dbg_nosync = ctx->dbg_nosync; p.l2_ahead_tiles = ctx->l2_ahead; p.hop_settle_ns = ctx->hop_settle; p.hop_hold = ctx->hop_hold; p.hop_near = ctx->hop_near; p.hop_near_ao = ctx->hop_near_ao;
-        CK(launch_decode_mega(p, ctx->grid, st));
+        if (B == 1) CK(launch_decode_mega(p, ctx->grid, st));
+        else CK(launch_decode_batch(p, ctx->grid, st));
+        ctx->gs_cur ^= 1;
         ctx->nlaunch += 1;
         ctx->n_host = std::min(max_total, ctx->n_host + n_steps);
         ctx->pending = false;
@@ -673,7 +728,7 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         a.ids_out = reinterpret_cast<long long*>(ids_out_dev) + (size_t)i * B;
         a.latents_out = latents_out_dev + (size_t)i * B * D;
         a.logits_out = logits_out_dev ? logits_out_dev + (size_t)i * B * V : nullptr;
-        a.status = status_dev; a.step_in_call = i;
+        a.status = status_dev; a.bad_ids = ctx->at<int>(ctx->o_flags); a.step_in_call = i;
         CK(launch_sample(a, B, st, &ctx->nlaunch));
         ctx->n_host = n + 1;
         ctx->pending = false;
@@ -687,6 +742,8 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
 int genvc_forward_latents(genvc_ctx* ctx, const float* cond_dev, const int64_t* text_ids_dev, int T, const int64_t* codes_dev,
                           int M, int B, float* latents_out_dev, void* stream) {
     if (int rc = check_ready(ctx)) return rc;
+    DevGuard guard(ctx->device);
+    CK(guard.err);
     const genvc_config& g = ctx->cfg;
     if (!cond_dev || !text_ids_dev || !codes_dev || !latents_out_dev) return ctx->fail(GENVC_E_INVALID, "null pointer");
     const int NLp = g.pc_latents, D = g.d_model;
@@ -699,9 +756,10 @@ int genvc_forward_latents(genvc_ctx* ctx, const float* cond_dev, const int64_t* 
     float* X = ctx->at<float>(ctx->o_X);
     // rows = [cond (32) ; text (T+2) ; start, codes, stop x4 (M+5)]
     CK(launch_embed_prefix(cond_dev, reinterpret_cast<const long long*>(text_ids_dev), B, T, NLp, D, ctx->w(L.text_emb),
-                           ctx->w(L.text_pos), g.start_text, g.stop_text, X, (long)R * D, st, &ctx->nlaunch));
+                           ctx->w(L.text_pos), g.start_text, g.stop_text, X, (long)R * D, g.n_text_vocab, ctx->at<int>(ctx->o_flags) + 1, st, &ctx->nlaunch));
     CK(launch_embed_mel_rows(reinterpret_cast<const long long*>(codes_dev), B, RM, M, g.start_audio, g.stop_audio, 0, D,
-                             ctx->w(L.mel_emb), ctx->w(L.mel_pos), X + (size_t)(NLp + RT) * D, (long)R * D, st, &ctx->nlaunch));
+                             ctx->w(L.mel_emb), ctx->w(L.mel_pos), X + (size_t)(NLp + RT) * D, (long)R * D, g.n_audio_vocab,
+                             ctx->at<int>(ctx->o_flags) + 1, st, &ctx->nlaunch));
     if (int rc = run_blocks(ctx, B, R, -1, nullptr, st)) return rc;
     // final_norm(ln_f(h)) of the first M mel rows of each element
     CK(launch_layernorm(X + (size_t)(NLp + RT) * D, D, (long)R * D, latents_out_dev, D, (long)M * D, B * M, M, D, ctx->w(L.lnf_w),

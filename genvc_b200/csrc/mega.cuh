@@ -40,8 +40,14 @@ struct MegaParams {
     unsigned tag0;   // first exchange tag of this launch (never 0; never reused while data with it is live)
     float* pend_logits;  // [V]
     float* pend_latent;  // [D]
-    GenState* st;
-    unsigned char* seen;  // [Vpad]
+    // generation state, double-buffered: a launch READS st / seen and WRITES st_out / seen_out (every CTA reads the
+    // state at kernel start with no grid-wide ordering, so the launch must not overwrite what it reads)
+    const GenState* st;
+    const unsigned char* seen;  // [B][Vpad]
+    GenState* st_out;
+    unsigned char* seen_out;    // [B][Vpad]
+    int B;         // rows (decode_batch.cu: 1..GV_BATCH_ROWS; decode_mega.cu: 1)
+    float* tokx;   // [GV_BATCH_ROWS] sampled tokens of the step, tagged (decode_batch.cu: row r is sampled by CTA r)
     // sampling
     int top_k;
     float top_p, top_p_threshold, temperature, rep_penalty;
@@ -53,7 +59,8 @@ struct MegaParams {
     long long* ids_out;   // [n_steps]
     float* latents_out;   // [n_steps, D]
     float* logits_out;    // [n_steps, V] or null
-    int* status;          // {emitted, done}
+    int* status;          // {emitted, done, out-of-range ids seen, reserved}
+    int* bad_ids;         // workspace flag set by the embedding kernels when they clamp an id (read + cleared by CTA 0)
     // debug timeline: tid 0 of every CTA stamps %globaltimer at phase boundaries of step `trace_step`
     unsigned long long* trace;  // [grid][trace_slots] or null
     int trace_step, trace_slots;
@@ -66,7 +73,15 @@ struct MegaParams {
     int dbg_nosync;  // consumers do not wait for exchange data (results are garbage; streaming-rate probe)
 };
 
+// rows the batched fused kernel decodes per pass of the weight stream (one mma n-tile)
+#define GV_BATCH_ROWS 8
+#define GV_BATCH_NSLOT 10  // ring depth of the batched kernel (its row buffers take the rest of shared memory)
+// exchange tags of one step of the batched kernel: the forward's tags + one for the sampled tokens
+#define GV_BATCH_TAGS_EXTRA 1
+
 size_t mega_smem_bytes(int D, int Vpad);
+size_t batch_smem_bytes(int D, int Vpad);
+cudaError_t launch_decode_batch(const MegaParams& p, int grid, cudaStream_t st);
 cudaError_t launch_decode_mega(const MegaParams& p, int grid, cudaStream_t st);
 cudaError_t launch_pack_stream(const StreamDims& s, int layer, int ph, const float* W, const float* bias, int w_nk,
                                const float* lnw, const float* lnb, float* stream, cudaStream_t st);

@@ -554,7 +554,7 @@ cudaError_t launch_kv_scatter(const float* qkv, int B, int M, int D, int H, floa
 __global__ void embed_prefix_kernel(const float* __restrict__ cond, const long long* __restrict__ text_ids, int B, int T,
                                     int n_lat, int D, const float* __restrict__ text_emb,
                                     const float* __restrict__ text_pos, int start_text, int stop_text,
-                                    float* __restrict__ out, long out_bs) {
+                                    float* __restrict__ out, long out_bs, int n_vocab, int* bad) {
     const int P = n_lat + T + 2;
     const int row = blockIdx.x;  // b * P + r
     const int b = row / P, r = row % P;
@@ -565,6 +565,10 @@ __global__ void embed_prefix_kernel(const float* __restrict__ cond, const long l
     } else {
         const int j = r - n_lat;  // position in [start, codes..., stop]
         long long id = (j == 0) ? start_text : (j == T + 1 ? stop_text : text_ids[(size_t)b * T + (j - 1)]);
+        if (id < 0 || id >= n_vocab) {  // the C ABI never reads outside the table: clamp, and flag it for the next status read
+            id = id < 0 ? 0 : n_vocab - 1;
+            if (bad != nullptr && threadIdx.x == 0) atomicOr(bad, 1);
+        }
         const float* e = text_emb + (size_t)id * D;
         const float* p = text_pos + (size_t)j * D;
         for (int i = threadIdx.x; i < D; i += blockDim.x) o[i] = e[i] + p[i];
@@ -572,27 +576,33 @@ __global__ void embed_prefix_kernel(const float* __restrict__ cond, const long l
 }
 cudaError_t launch_embed_prefix(const float* cond, const long long* text_ids, int B, int T, int n_lat, int D,
                                 const float* text_emb, const float* text_pos, int start_text, int stop_text, float* out,
-                                long out_bs, cudaStream_t st, unsigned long long* nlaunch) {
+                                long out_bs, int n_vocab, int* bad, cudaStream_t st, unsigned long long* nlaunch) {
     embed_prefix_kernel<<<B * (n_lat + T + 2), 128, 0, st>>>(cond, text_ids, B, T, n_lat, D, text_emb, text_pos,
-                                                             start_text, stop_text, out, out_bs);
+                                                             start_text, stop_text, out, out_bs, n_vocab, bad);
     GV_BUMP(nlaunch);
     return cudaGetLastError();
 }
 
 __global__ void embed_mel_rows_kernel(const long long* __restrict__ codes, int B, int R, int M, int first_tok, int pad_tok,
                                       int pos0, int D, const float* __restrict__ mel_emb,
-                                      const float* __restrict__ mel_pos, float* __restrict__ out, long out_bs) {
+                                      const float* __restrict__ mel_pos, float* __restrict__ out, long out_bs, int n_vocab,
+                                      int* bad) {
     const int b = blockIdx.x / R, r = blockIdx.x % R;
     long long id = (r == 0) ? first_tok : ((codes && r - 1 < M) ? codes[(size_t)b * M + (r - 1)] : pad_tok);
+    if (id < 0 || id >= n_vocab) {
+        id = id < 0 ? 0 : n_vocab - 1;
+        if (bad != nullptr && threadIdx.x == 0) atomicOr(bad, 1);
+    }
     const float* e = mel_emb + (size_t)id * D;
     const float* p = mel_pos + (size_t)(pos0 + r) * D;
     float* o = out + (size_t)b * out_bs + (size_t)r * D;
     for (int i = threadIdx.x; i < D; i += blockDim.x) o[i] = e[i] + p[i];
 }
 cudaError_t launch_embed_mel_rows(const long long* codes, int B, int R, int M, int first_tok, int pad_tok, int pos0, int D,
-                                  const float* mel_emb, const float* mel_pos, float* out, long out_bs, cudaStream_t st,
-                                  unsigned long long* nlaunch) {
-    embed_mel_rows_kernel<<<B * R, 128, 0, st>>>(codes, B, R, M, first_tok, pad_tok, pos0, D, mel_emb, mel_pos, out, out_bs);
+                                  const float* mel_emb, const float* mel_pos, float* out, long out_bs, int n_vocab, int* bad,
+                                  cudaStream_t st, unsigned long long* nlaunch) {
+    embed_mel_rows_kernel<<<B * R, 128, 0, st>>>(codes, B, R, M, first_tok, pad_tok, pos0, D, mel_emb, mel_pos, out, out_bs,
+                                                 n_vocab, bad);
     GV_BUMP(nlaunch);
     return cudaGetLastError();
 }
@@ -730,7 +740,11 @@ __global__ void __launch_bounds__(GV_SAMPLE_THREADS) sample_kernel(SampleArgs a,
     const int n = st->n_emitted;
     int tok = sample_token([&](int e) { return ldcg(lg + e); }, seen, c, a.noise ? a.noise + (size_t)b * a.V : nullptr, a.seed, (uint32_t)n, (uint32_t)b,
                            keys, fscr, iscr, tid, BlockSync());
-    if (a.forced) tok = (int)a.forced[b];
+    if (a.forced) {
+        const long long f = a.forced[b];
+        tok = (f >= 0 && f < (long long)a.V) ? (int)f : a.stop_token;  // out-of-range ids never index seen[] / mel_emb
+        if (tok != (int)f && tid == 0 && a.bad_ids != nullptr) atomicOr(a.bad_ids, 1);
+    }
     const int was_finished = st->finished[b];
     if (!a.ignore_eos && was_finished) tok = a.stop_token;  // finished rows emit the pad (== eos) token
     // emit (token, latent[, logits]) — the yield of sample_stream happens before the EOS test
@@ -753,6 +767,7 @@ __global__ void __launch_bounds__(GV_SAMPLE_THREADS) sample_kernel(SampleArgs a,
             st->n_emitted = n + 1;
             st->has_pending = 0;
             a.status[0] = a.step_in_call + 1;
+            if (a.bad_ids != nullptr && atomicExch(a.bad_ids, 0) != 0) a.status[2] = 1;  // out-of-range ids since the last status
             if (all_fin || n + 1 >= a.max_total) {
                 st->done = 1;
                 a.status[1] = 1;

@@ -79,7 +79,8 @@ struct SampleArgs {
     long long* ids_out;           // [B]
     float* latents_out;           // [B,D]
     float* logits_out;            // [B,V] or null
-    int* status;                  // {emitted this call, done}
+    int* status;                  // {emitted this call, done, out-of-range ids seen, reserved}
+    int* bad_ids;                 // workspace flag set by the embedding kernels when they clamp an id (read + cleared here)
     int step_in_call;
 };
 
@@ -105,12 +106,12 @@ cudaError_t launch_kv_scatter(const float* qkv, int B, int M, int D, int H, floa
                               int S_max, int pos0, const int* skip, cudaStream_t st, unsigned long long* nlaunch);
 cudaError_t launch_embed_prefix(const float* cond, const long long* text_ids, int B, int T, int n_lat, int D,
                                 const float* text_emb, const float* text_pos, int start_text, int stop_text, float* out,
-                                long out_bs, cudaStream_t st, unsigned long long* nlaunch);
+                                long out_bs, int n_vocab, int* bad, cudaStream_t st, unsigned long long* nlaunch);
 // rows of [tokens] with mel embeddings: out[b, r, :] = mel_emb[tok(b,r)] + mel_pos[pos0 + r]
 // tok(b,r): r == 0 ? first_tok : (codes ? (r-1 < M ? codes[b, r-1] : pad_tok) : n/a)
 cudaError_t launch_embed_mel_rows(const long long* codes, int B, int R, int M, int first_tok, int pad_tok, int pos0, int D,
-                                  const float* mel_emb, const float* mel_pos, float* out, long out_bs, cudaStream_t st,
-                                  unsigned long long* nlaunch);
+                                  const float* mel_emb, const float* mel_pos, float* out, long out_bs, int n_vocab, int* bad,
+                                  cudaStream_t st, unsigned long long* nlaunch);
 cudaError_t launch_embed_last_token(const GenState* stt, int B, int pos, int D, const float* mel_emb, const float* mel_pos,
                                     float* out, cudaStream_t st, unsigned long long* nlaunch);
 cudaError_t launch_copy_rows(const float* src, long src_bs, float* dst, long dst_bs, int B, long row_floats, cudaStream_t st,

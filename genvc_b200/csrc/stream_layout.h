@@ -86,5 +86,16 @@ GV_HD int att_chunk(int S) {
     return (c + 15) / 16 * 16;
 }
 GV_HD int att_nsplit(int S) { return (S + att_chunk(S) - 1) / att_chunk(S); }
+// batched kernel: items = rows * H * nsplit must fit the grid (BH = rows * H <= G): at most G / BH key ranges per
+// (row, head); chunk = keys per range (multiple of 16), actual nsplit = ceil(S / chunk)
+GV_HD int att_nsplit_b(int S, int BH, int G) {
+    const int ns = att_nsplit(S), cap = G / BH > 1 ? G / BH : 1;
+    return ns < cap ? ns : cap;
+}
+GV_HD int att_chunk_b(int S, int nsplit) {
+    int c = (S + nsplit - 1) / nsplit;
+    if (c < 32) c = 32;
+    return (c + 15) / 16 * 16;
+}
 
 }  // namespace gv

@@ -55,7 +55,7 @@ class DecodeChunk:
     ids: torch.Tensor  # [n_steps, B] int64
     latents: torch.Tensor  # [n_steps, B, D] fp32
     logits: Optional[torch.Tensor]  # [n_steps, B, V] raw logits, if requested
-    status: torch.Tensor  # int32 [2] = {steps emitted by this call, done}
+    status: torch.Tensor  # int32 [4] = {steps emitted by this call, done, out-of-range ids were clamped, reserved}
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -131,9 +131,11 @@ class Engine:
         return t.contiguous()
 
     def _check_ids(self, ids: torch.Tensor, vocab: int, what: str):
-        """Range check (the kernels index embedding tables with these).  Free for host tensors;
-        one device sync for device tensors unless ``validate_device_ids`` is switched off."""
-        if ids.numel() == 0 or (ids.is_cuda and not self.validate_device_ids):
+        """Range check of ids the kernels index embedding tables with.  Host tensors are checked here (free).
+        Device tensors are NOT synchronised on: the kernels clamp an out-of-range id (no out-of-bounds read) and
+        raise a flag that comes back with the next decode status (``DecodeChunk.status[2]``; ``GPT`` turns it
+        into an ``IndexError``).  ``validate_device_ids = "sync"`` restores the blocking check."""
+        if ids.numel() == 0 or (ids.is_cuda and self.validate_device_ids != "sync"):
             return
         lo, hi = int(ids.min()), int(ids.max())
         if lo < 0 or hi >= vocab:
@@ -142,6 +144,10 @@ class Engine:
     @property
     def decode_grid(self) -> int:
         return int(self.lib.genvc_decode_grid(self._ctx))
+
+    def fused_rows(self, B: int) -> bool:
+        """True when a batch of ``B`` rows runs through a fused persistent decode kernel (decode_mega / decode_batch)."""
+        return self.wstream is not None and 1 <= B <= int(self.lib.genvc_fused_max_rows(self._ctx))
 
     @property
     def launch_count(self) -> int:
@@ -222,14 +228,17 @@ class Engine:
             if tuple(noise.shape) != (n_steps, B, V):
                 raise ValueError(f"noise must be [{n_steps}, {B}, {V}]")
         if forced is not None:
+            self._check_ids(forced, V, "forced token id")
             forced = self._dev(forced, torch.int64, "forced")
             if tuple(forced.shape) != (n_steps, B):
                 raise ValueError(f"forced ids must be [{n_steps}, {B}]")
         dev = self.device
-        ids = torch.full((n_steps, B), self.dims.stop_audio, dtype=torch.int64, device=dev)
-        lat = torch.zeros((n_steps, B, D), dtype=torch.float32, device=dev)
-        lg = torch.zeros((n_steps, B, V), dtype=torch.float32, device=dev) if want_logits else None
-        status = torch.zeros(2, dtype=torch.int32, device=dev)
+        # No fill kernels: the library zeroes `status` on the stream and only the first status[0] steps of the
+        # outputs are defined (every consumer slices by it).
+        ids = torch.empty((n_steps, B), dtype=torch.int64, device=dev)
+        lat = torch.empty((n_steps, B, D), dtype=torch.float32, device=dev)
+        lg = torch.empty((n_steps, B, V), dtype=torch.float32, device=dev) if want_logits else None
+        status = torch.empty(4, dtype=torch.int32, device=dev)
         sp = sampling.to_c()
         ev = None
         if self.timing is not None:

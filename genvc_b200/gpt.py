@@ -153,8 +153,10 @@ class GPT:
             raise NotImplementedError("beam search is not part of the GenVC path (num_beams must be 1)")
         if kw.get("num_return_sequences", 1) not in (None, 1):
             raise NotImplementedError("num_return_sequences must be 1")
-        do_sample = kw.get("do_sample", True)
-        top_k = kw.get("top_k", 50)  # HF GenerationConfig default
+        # HF GenerationConfig defaults: do_sample=False (greedy) -- a bare ``generate(cond, text)`` like the reference's
+        # own ``self.generate(cond_latent_cv, text_input_cv)`` is greedy; the inference drivers pass do_sample=True
+        do_sample = kw.get("do_sample", False)
+        top_k = kw.get("top_k", 50)
         top_p = kw.get("top_p", 1.0)
         temperature = kw.get("temperature", 1.0)
         if not do_sample:
@@ -186,57 +188,27 @@ class GPT:
         noise, forced = kw.get("exp_noise"), kw.get("forced_ids")
         mode = int(kw.get("decode_mode", 0))
         B = int(text_inputs.shape[0])
-        if mode == 0 and 1 < B <= self.ROWWISE_MAX_BATCH and eng.wstream is not None:
-            return self._generate_rowwise(cond_latents, text_inputs, generate_kwargs, sp.seed)
         self.compute_embeddings(cond_latents, text_inputs)
         eng.prefill(self._prefix)
         cap = self._cap(sp)
-        fused = mode == 2 or (mode == 0 and B == 1 and eng.wstream is not None)
-        # the fused kernel runs the whole loop in one launch; the per-op path is enqueued in slices so an
-        # early EOS does not leave hundreds of skipped launches behind
+        fused = mode == 2 or (mode == 0 and eng.fused_rows(B))
+        # the fused kernels (one row: decode_mega; 2..8 rows: decode_batch) run the whole loop in one launch; the per-op
+        # path is enqueued in slices so an early EOS does not leave hundreds of skipped launches behind
         step = cap if fused else 32
         ids, lats, done, n = [], [], False, 0
         while not done and n < cap:
             k = min(step, cap - n)
             ch = eng.decode(k, sp, None if noise is None else noise[n:n + k], None if forced is None else forced[n:n + k],
                             mode=mode)
-            emitted, done_flag = ch.status.tolist()  # host sync
+            emitted, done_flag, bad = ch.status.tolist()[:3]  # host sync
+            if bad:
+                raise IndexError("a text or forced token id was outside its vocabulary (clamped on the device)")
             ids.append(ch.ids[:emitted])
             lats.append(ch.latents[:emitted])
             n += emitted
             done = bool(done_flag) or emitted < k
         out = torch.cat(ids, 0).transpose(0, 1).contiguous()
         self.last_latents = torch.cat(lats, 0).transpose(0, 1).contiguous()
-        return out
-
-    # Small batches: the fused single-row kernel (0.42 ms/token) run row after row beats the batched per-op path
-    # (~3.5 ms per step for 1-8 rows, launch-latency bound) up to 8 rows; 4 keeps a margin (tools/batch_bench.py).
-    ROWWISE_MAX_BATCH = 4
-
-    def _generate_rowwise(self, cond_latents, text_inputs, generate_kwargs, seed: int) -> torch.Tensor:
-        """Rows are independent (no cross-row state in HF ``sample``): each one through the fused kernel; a finished row
-        is padded with ``stop_audio_token`` until the longest row ends, as the batched loop does.  Greedy decoding and
-        caller-injected multinomial noise give exactly the batched path's tokens; the on-device Philox stream is keyed
-        per row from the call's seed (reproducible, but not the stream ``decode_mode=1`` draws for the same seed)."""
-        B = int(text_inputs.shape[0])
-        noise, forced = generate_kwargs.get("exp_noise"), generate_kwargs.get("forced_ids")
-        ids, lats = [], []
-        for b in range(B):
-            kw = dict(generate_kwargs)
-            kw["seed"] = (int(seed) + b * 0x9E3779B97F4A7C15) & 0x3FFFFFFFFFFFFFFF
-            if noise is not None:
-                kw["exp_noise"] = noise[:, b:b + 1].contiguous()
-            if forced is not None:
-                kw["forced_ids"] = forced[:, b:b + 1].contiguous()
-            ids.append(self.generate(cond_latents[b:b + 1], text_inputs[b:b + 1], **kw)[0])
-            lats.append(self.last_latents[0])
-        n = max(int(t.shape[0]) for t in ids)
-        out = torch.full((B, n), self.stop_audio_token, dtype=torch.long, device=ids[0].device)
-        lat = torch.zeros((B, n, lats[0].shape[-1]), dtype=lats[0].dtype, device=lats[0].device)
-        for b in range(B):
-            out[b, : ids[b].shape[0]] = ids[b]
-            lat[b, : lats[b].shape[0]] = lats[b]
-        self.last_latents = lat
         return out
 
     def inference(self, cond_latents, text_inputs, **generate_kwargs):
@@ -285,7 +257,7 @@ class GPT:
             with torch.cuda.stream(gs):
                 ch = eng.decode(k, sp, None if noise is None else noise[n0:n0 + k],
                                 None if forced is None else forced[n0:n0 + k], mode=mode)
-                host_status = torch.empty(2, dtype=torch.int32, pin_memory=True)
+                host_status = torch.empty(4, dtype=torch.int32, pin_memory=True)
                 host_status.copy_(ch.status, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(gs)
@@ -303,6 +275,8 @@ class GPT:
                 for t in (ch.ids, ch.latents):
                     t.record_stream(caller)
                 emitted, done = int(host_status[0]), int(host_status[1])
+                if int(host_status[2]):
+                    raise IndexError("a text or forced token id was outside its vocabulary (clamped on the device)")
                 for i in range(emitted):
                     yield ch.ids[i], ch.latents[i]
                 n += emitted

@@ -49,6 +49,7 @@ SIGNATURES = {
     "genvc_destroy": (None, [_P]),
     "genvc_last_error": (C.c_char_p, [_P]),
     "genvc_decode_grid": (C.c_int, [_P]),
+    "genvc_fused_max_rows": (C.c_int, [_P]),
     "genvc_blob_floats": (C.c_uint64, [_P]),
     "genvc_num_tensors": (C.c_int, [_P]),
     "genvc_tensor_name": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_size_t]),

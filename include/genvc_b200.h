@@ -83,6 +83,10 @@ void genvc_destroy(genvc_ctx* ctx);
 const char* genvc_last_error(const genvc_ctx* ctx);
 /* Number of SMs the fused decode kernel will occupy (one persistent CTA each). */
 int genvc_decode_grid(const genvc_ctx* ctx);
+/* Largest batch the fused persistent decode kernels take in one launch: 0 (shape unsupported: per-op kernels only),
+ * 1 (single-row kernel) or up to 8 (batched kernel: rows share one pass of the weight stream; equal-length rows with
+ * a shared position index as layers/gpt_inference.py:92-96, finished rows padded as layers/stream_generator.py:860-881). */
+int genvc_fused_max_rows(const genvc_ctx* ctx);
 
 /* ---- weights: checkpoint layout -> device blob ---------------------------- *
  * Replaces model.load_state_dict(...).to(device) for the `gpt.*` keys
@@ -150,8 +154,10 @@ int genvc_prefill(genvc_ctx* ctx, const float* prefix_dev, int B, int P, void* s
  *                   (teacher forcing for logits parity), or NULL.
  *   ids_out_dev   : [n_steps,B] int64;  latents_out_dev: [n_steps,B,D];
  *   logits_out_dev: [n_steps,B,V] raw logits before processing, or NULL.
- *   status_dev    : int32[2] = {steps emitted by this call, done flag}.
- *   mode          : 0 auto, 1 per-op kernels, 2 fused persistent kernel (B==1). */
+ *   status_dev    : int32[4] = {steps emitted by this call, done flag, bad-id flag, reserved}.  The bad-id flag is 1
+ *                   when a text id (genvc_embed_prefix) or a forced id since the previous status was outside its
+ *                   vocabulary: the kernels clamp such ids (no out-of-bounds read) and report them here.
+ *   mode          : 0 auto, 1 per-op kernels, 2 fused persistent kernel (B <= genvc_fused_max_rows). */
 int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp,
                  const float* exp_noise_dev, const int64_t* forced_ids_dev,
                  int64_t* ids_out_dev, float* latents_out_dev, float* logits_out_dev,

@@ -51,6 +51,23 @@ CASES = {
                             top_k=1, top_p=0.85, new_tokens=64, keep_all=False, full=True),
     "full_h4_topk20": dict(model=dict(n_layer=30, d_model=1024, n_head=4, seed=1234), T=75, S_mel=469, B=1,
                            top_k=20, top_p=0.85, new_tokens=48, keep_all=False, full=True, noise_seed=79),
+    # ---- round 2: batches (BASELINE configs[2]/[3]: equal-T rows, shared position index, finished rows padded) ----
+    "toy_d128_batch8_eos": dict(model=dict(n_layer=2, d_model=128, n_head=4, seed=3, eos_bias=1.5), T=11, S_mel=90, B=8,
+                                top_k=1, top_p=0.85, new_tokens=96, keep_all=True),
+    "toy_d256_batch5_topk20": dict(model=dict(n_layer=3, d_model=256, n_head=4, seed=4), T=20, S_mel=100, B=5,
+                                   top_k=20, top_p=0.85, new_tokens=40, keep_all=True, noise_seed=80),
+    "full_h4_batch4_greedy": dict(model=dict(n_layer=30, d_model=1024, n_head=4, seed=1234), T=25, S_mel=282, B=4,
+                                  top_k=1, top_p=0.85, new_tokens=20, keep_all=False, full=True),
+    "full_h4_batch8_topk20": dict(model=dict(n_layer=30, d_model=1024, n_head=4, seed=1234), T=50, S_mel=469, B=8,
+                                  top_k=20, top_p=0.85, new_tokens=40, keep_all=False, full=True, noise_seed=81),
+    "full_h16_batch8_greedy": dict(model=dict(n_layer=30, d_model=1024, n_head=16, seed=1234), T=13, S_mel=282, B=8,
+                                   top_k=1, top_p=0.85, new_tokens=24, keep_all=False, full=True),
+    # shipped sampling defaults (top_k 15) on the 6 s reference chunk the pipeline produces (563 mel frames)
+    "full_h4_topk15_mel563": dict(model=dict(n_layer=30, d_model=1024, n_head=4, seed=1234), T=75, S_mel=563, B=1,
+                                  top_k=15, top_p=0.85, new_tokens=40, keep_all=False, full=True, noise_seed=82),
+    # "GenVC_large": same dimensions (the README distinguishes the two checkpoints by training data only), second seed
+    "full_large_seed4321": dict(model=dict(n_layer=30, d_model=1024, n_head=4, seed=4321), T=38, S_mel=282, B=2,
+                                top_k=1, top_p=0.85, new_tokens=32, keep_all=False, full=True),
 }
 
 

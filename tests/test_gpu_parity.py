@@ -17,7 +17,9 @@ LOGIT_ATOL, LOGIT_RTOL = 1e-3, 1e-4
 LAT_ATOL, LAT_RTOL = 1e-4, 1e-4
 TOY = ["toy_d128_greedy", "toy_d128_topk20", "toy_d128_topk0_topp1", "toy_d128_eos", "toy_d256_h4_greedy",
        "toy_d512_h2_greedy"]
-FULL = ["full_h4_cfg1", "full_h16_greedy", "full_h4_topk20"]
+FULL = ["full_h4_cfg1", "full_h16_greedy", "full_h4_topk20", "full_h4_topk15_mel563"]
+TOY_BATCH = ["toy_d128_batch3", "toy_d128_batch8_eos", "toy_d256_batch5_topk20"]
+FULL_BATCH = ["full_h4_batch4_greedy", "full_h4_batch8_topk20", "full_h16_batch8_greedy", "full_large_seed4321"]
 
 _GPT_CACHE = {}
 
@@ -116,7 +118,7 @@ def test_teacher_forced_logits(name, mode, cuda_device):
     sp = Sampling(**fx["sampling"], max_new_tokens=n)
     forced = fx["ids"][:, :n].transpose(0, 1).contiguous().to(cuda_device)
     ch = eng.decode(n, sp, forced=forced, want_logits=True, mode=mode)
-    emitted, _ = ch.status.tolist()
+    emitted = ch.status.tolist()[0]
     assert emitted == n
     assert torch.equal(ch.ids.cpu(), forced.cpu())
     steps = fx["steps"][fx["steps"] < n]
@@ -148,7 +150,7 @@ def test_fused_long_context_matches_per_op(name, T, n, cuda_device):
         g.compute_embeddings(cond, codes)
         eng.prefill(g._prefix)
         ch = eng.decode(n, sp, forced=forced, want_logits=True, mode=mode)
-        emitted, _ = ch.status.tolist()
+        emitted = ch.status.tolist()[0]
         assert emitted == n
         assert torch.equal(ch.ids.cpu(), forced.cpu())
         out[mode] = (ch.logits.clone(), ch.latents.clone())
@@ -176,19 +178,132 @@ def test_full_size_per_op_prefix_matches(cuda_device):
     assert torch.equal(ids.cpu(), fx["ids"][:, :40])
 
 
-def test_batched_rows_equal_reference(cuda_device):
-    """A7: equal-T batch through the per-op path; rows finish at different steps and are padded with 1025."""
-    fx = load_golden("toy_d128_batch3")
-    g = make_gpt(fx, cuda_device, max_batch=3)
+@pytest.mark.parametrize("mode", [1, 2, 0], ids=["per_op", "fused_batch", "auto"])
+@pytest.mark.parametrize("name", TOY_BATCH)
+def test_toy_batched_rows_equal_reference(name, mode, cuda_device):
+    """A7 / layers/stream_generator.py:860-881: equal-T batches; rows finish at different steps and are padded with
+    1025.  Fixtures come from the reference modules run on the whole batch; per-op kernels and the batched fused
+    kernel (rows share one pass of the weight stream) must both reproduce ids bit-exactly."""
+    fx = load_golden(name)
+    B = fx["ids"].shape[0]
+    g = make_gpt(fx, cuda_device, max_batch=B)
     out = g.get_style_emb(fx["mel"].to(cuda_device))
     ok, err = close(out, fx["style_emb"], 2e-4, 1e-4)
     assert ok, err
-    for mode in (1, 0):  # batched per-op path, then the default (row by row through the fused kernel)
-        ids, lats = _run_generate(fx, g, cuda_device, mode)
-        assert torch.equal(ids.cpu(), fx["ids"]), f"mode {mode}"
-        if mode == 1:  # rows that finished keep producing (discarded) latents in the batched loop only
-            ok, err = close(lats[:, fx["steps"].to(lats.device)], fx["latents"], LAT_ATOL, LAT_RTOL)
-            assert ok, f"latent max err {err}"
+    assert g.engine.fused_rows(B)
+    ids, lats = _run_generate(fx, g, cuda_device, mode)
+    assert torch.equal(ids.cpu(), fx["ids"]), f"mode {mode}: first mismatch at {(ids.cpu() != fx['ids']).nonzero()[:1].tolist()}"
+    ok, err = close(lats[:, fx["steps"].to(lats.device)], fx["latents"], LAT_ATOL, LAT_RTOL)
+    assert ok, f"latent max err {err}"
+
+
+@pytest.mark.parametrize("name", FULL_BATCH)
+def test_full_size_batched_fused_ids_bit_exact(name, cuda_device):
+    """BASELINE configs[2]/[3] shapes at L=30, D=1024 (B = 2, 4, 8; H = 4 and 16; greedy and top-k 20 with injected
+    multinomial noise; second-seed "large" checkpoint): free-running ids of the batched fused kernel against
+    fixtures generated by the reference modules on the whole batch."""
+    fx = load_golden(name)
+    B = fx["ids"].shape[0]
+    g = make_gpt(fx, cuda_device, max_batch=B)
+    ids, lats = _run_generate(fx, g, cuda_device, 2)
+    assert ids.shape == fx["ids"].shape
+    assert torch.equal(ids.cpu(), fx["ids"]), f"first mismatch at {(ids.cpu() != fx['ids']).nonzero()[:1].tolist()}"
+    ok, err = close(lats[:, fx["steps"].to(lats.device)], fx["latents"], LAT_ATOL, LAT_RTOL)
+    assert ok, f"latent max err {err}"
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["per_op", "fused_batch"])
+@pytest.mark.parametrize("name", TOY_BATCH + FULL_BATCH)
+def test_batched_teacher_forced_logits(name, mode, cuda_device):
+    """Logits and latents of every row at every step with the reference's tokens forced."""
+    fx = load_golden(name)
+    B, n = fx["ids"].shape
+    g = make_gpt(fx, cuda_device, max_batch=B)
+    eng = g.engine
+    cond = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device)
+    g.compute_embeddings(cond, fx["codes"].to(cuda_device))
+    eng.prefill(g._prefix)
+    from genvc_b200.engine import Sampling
+
+    # ignore_eos: rows that finished keep being fed the fixture's (pad) tokens, as the reference's loop does
+    sp = Sampling(**fx["sampling"], max_new_tokens=n, ignore_eos=True)
+    forced = fx["ids"].transpose(0, 1).contiguous().to(cuda_device)
+    ch = eng.decode(n, sp, forced=forced, want_logits=True, mode=mode)
+    emitted = ch.status.tolist()[0]
+    assert emitted == n
+    assert torch.equal(ch.ids.cpu(), forced.cpu())
+    steps = fx["steps"]
+    got = ch.logits.transpose(0, 1)[:, steps.to(cuda_device)]
+    ok, err = close(got, fx["logits"], LOGIT_ATOL, LOGIT_RTOL)
+    assert ok, f"logit max err {err}"
+    ok, err = close(ch.latents.transpose(0, 1)[:, steps.to(cuda_device)], fx["latents"], LAT_ATOL, LAT_RTOL)
+    assert ok, f"latent max err {err}"
+
+
+def test_batched_fused_long_context_matches_per_op(cuda_device):
+    """Batched fused kernel at long contexts (S up to ~760: several key ranges per (row, head) item, capped by
+    grid / (rows * heads)) against the per-op path, forced random tokens, B = 3 and 8."""
+    from genvc_b200.engine import Sampling
+
+    for name, B, T, n in (("toy_d256_h4_greedy", 8, 400, 330), ("full_h4_cfg1", 3, 240, 24)):
+        fx = load_golden(name)
+        g = make_gpt(fx, cuda_device, max_batch=B)
+        eng = g.engine
+        gen = torch.Generator().manual_seed(98)
+        codes = torch.randint(0, 256, (B, T), generator=gen).to(cuda_device)
+        cond = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device).expand(B, -1, -1).contiguous()
+        forced = torch.randint(0, 1024, (n, B), generator=gen).to(cuda_device)
+        sp = Sampling(**fx["sampling"], max_new_tokens=n)
+        out = {}
+        for mode in (1, 2):
+            g.compute_embeddings(cond, codes)
+            eng.prefill(g._prefix)
+            ch = eng.decode(n, sp, forced=forced, want_logits=True, mode=mode)
+            assert ch.status.tolist()[0] == n
+            out[mode] = (ch.logits.clone(), ch.latents.clone())
+        ok, err = close(out[2][0], out[1][0], LOGIT_ATOL, LOGIT_RTOL)
+        assert ok, f"{name}: logit max err {err}"
+        ok, err = close(out[2][1], out[1][1], LAT_ATOL, LAT_RTOL)
+        assert ok, f"{name}: latent max err {err}"
+
+
+@pytest.mark.parametrize("name", ["toy_d128_greedy", "toy_d128_batch3"])
+def test_chunk_size_one_greedy(name, cuda_device):
+    """stream_chunk_size = 1: the first launch after a prefill runs no forward at all (it samples from the prefill's
+    logits), so CTA 0 can finish while other CTAs are still reading the generation state -- the state is
+    double-buffered for exactly this (a launch never writes what it reads)."""
+    fx = load_golden(name)
+    B = fx["ids"].shape[0]
+    g = make_gpt(fx, cuda_device, max_batch=B)
+    cond = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device)
+    for _ in range(3):
+        fake = g.compute_embeddings(cond, fx["codes"].to(cuda_device))
+        toks = [t for t, _ in g.get_generator(fake_inputs=fake, **gen_kwargs(fx, stream_chunk_size=1))]
+        ids = torch.stack(toks, 1).cpu()
+        assert torch.equal(ids, fx["ids"])
+
+
+def test_out_of_range_ids_are_flagged_not_read(cuda_device):
+    """C-ABI safety: ids outside the vocabulary never index a table out of bounds; device tensors are not synchronised
+    on, the kernels clamp and the flag comes back with the decode status."""
+    fx = load_golden("toy_d128_greedy")
+    g = make_gpt(fx, cuda_device)
+    cond = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device)
+    bad = fx["codes"].clone()
+    bad[0, 3] = 100000
+    with pytest.raises(IndexError):  # host tensor: checked before any launch
+        g.compute_embeddings(cond, bad)
+    with pytest.raises(IndexError):  # device tensor: flagged by the kernel, raised with the first chunk's status
+        g.generate(cond, bad.to(cuda_device), **gen_kwargs(fx))
+    from genvc_b200.engine import Sampling
+
+    g.compute_embeddings(cond, fx["codes"].to(cuda_device))
+    g.engine.prefill(g._prefix)
+    forced = torch.full((4, 1), 5000, dtype=torch.int64, device=cuda_device)
+    ch = g.engine.decode(4, Sampling(**fx["sampling"]), forced=forced, mode=2)
+    assert ch.status.tolist()[2] == 1
+    ids = g.generate(cond, fx["codes"].to(cuda_device), **gen_kwargs(fx))  # the engine is fine afterwards
+    assert torch.equal(ids.cpu(), fx["ids"])
 
 
 # ------------------------------------------------------------------------------------ latent pass
@@ -206,28 +321,6 @@ def test_latent_pass(name, cuda_device):
         lat = lat[:, fx["latent_pass_steps"].to(cuda_device)]
     ok, err = close(lat, fx["latent_pass"], LAT_ATOL, LAT_RTOL)
     assert ok, f"latent-pass max err {err}"
-
-
-def test_full_size_batch_rows_equal_single_row_fused(cuda_device):
-    """BASELINE configs[2]/[3] shape at L=30, D=1024: a batch of 4 different utterances (equal T) through the batched
-    per-op path gives, row by row, the ids the fused single-row kernel gives for the same inputs (greedy)."""
-    fx = load_golden("full_h4_cfg1")
-    gen = torch.Generator().manual_seed(21)
-    B, T, n = 4, 25, 20
-    codes = torch.randint(0, 256, (B, T), generator=gen).to(cuda_device)
-    cond1 = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device)
-    kw = dict(do_sample=True, top_p=0.85, top_k=1, temperature=0.85, num_beams=1, length_penalty=1.0,
-              repetition_penalty=2.0, output_attentions=False, max_new_tokens=n)
-    g1 = make_gpt(fx, cuda_device)
-    single = [g1.generate(cond1, codes[b:b + 1], decode_mode=2, **kw)[0].cpu() for b in range(B)]
-    gB = make_gpt(fx, cuda_device, max_batch=B)
-    for mode in (1, 0):  # 1: batched per-op kernels; 0: default (small batches go row by row through the fused kernel)
-        ids = gB.generate(cond1.expand(B, -1, -1).contiguous(), codes, decode_mode=mode, **kw).cpu()
-        assert ids.shape[0] == B
-        for b in range(B):
-            m = min(ids.shape[1], single[b].shape[0])
-            assert torch.equal(ids[b, :m], single[b][:m]), \
-                f"mode {mode} row {b}: first mismatch at {(ids[b, :m] != single[b][:m]).nonzero()[:1].tolist()}"
 
 
 # ------------------------------------------------------------------------------------ streaming protocol

@@ -8,7 +8,7 @@ from conftest import golden_checkpoint, load_golden
 from oracle.genvc_oracle import SamplingParams, draw_exponential_noise, load_oracle
 
 TOY = ["toy_d128_greedy", "toy_d128_topk20", "toy_d128_topk0_topp1", "toy_d128_eos", "toy_d128_batch3",
-       "toy_d256_h4_greedy", "toy_d512_h2_greedy"]
+       "toy_d256_h4_greedy", "toy_d512_h2_greedy", "toy_d128_batch8_eos", "toy_d256_batch5_topk20"]
 TOL = 2e-5
 
 
