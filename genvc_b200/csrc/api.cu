@@ -59,7 +59,8 @@ struct genvc_ctx {
     // workspace offsets (bytes)
     size_t o_state, o_seen, state_stride = 0, seen_stride = 0, o_tokx, o_flags, o_status_scratch, o_pend_logits, o_pend_latent, o_splitk, o_X, o_A, o_QKV, o_U;
     // exchange buffers of the fused decode kernel ({value, tag} pairs; one contiguous region)
-    size_t o_xchg, xchg_bytes, o_xq, o_matt_o, o_matt_ml, o_x1, o_pp, o_x2, o_lg, o_hops, o_acc;
+    size_t o_xchg, xchg_bytes, o_xq, o_matt_o, o_matt_ml, o_x1, o_pp, o_x2, o_lg, o_hops, o_acc, o_ao, o_attcnt;
+    size_t hops_bytes = 0;
     size_t acc_bytes = 0;
     uint32_t tag_next = 1;
     size_t o_pc_melT, o_pc_ctx, o_pc_kv, o_pc_lat, o_pc_q, o_pc_o, o_pc_h, o_pc_g;
@@ -152,7 +153,11 @@ static void plan_workspace(genvc_ctx* c) {
     c->o_x2 = w.take(2 * FR * D * F);
     c->o_lg = w.take(2 * FR * (size_t)c->Vpad * F);
     c->o_tokx = w.take(2 * GV_BATCH_ROWS * F);
+    c->o_ao = w.take(2 * FR * D * F);
+    // arrival counters (zeroed before every fused launch): the hop counters, then one item counter per (row, head)
     c->o_hops = w.take(HC_COUNT * GV_HOP_STRIDE * sizeof(unsigned));
+    c->o_attcnt = w.take((size_t)std::max(c->grid, 1) * GV_ATTCNT_STRIDE * sizeof(unsigned));
+    c->hops_bytes = w.take(0) - c->o_hops;
     c->acc_bytes = 2 * (size_t)g.n_layer * D * sizeof(unsigned long long);
     c->o_acc = w.take(c->acc_bytes);
     c->xchg_bytes = w.take(0) - c->o_xchg;
@@ -669,7 +674,8 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         p.x1 = ctx->at<float>(ctx->o_x1); p.pp = ctx->at<float>(ctx->o_pp); p.x2 = ctx->at<float>(ctx->o_x2);
         p.lg = ctx->at<float>(ctx->o_lg);
         p.hops = ctx->at<unsigned>(ctx->o_hops);
-        CK(cudaMemsetAsync(p.hops, 0, HC_COUNT * GV_HOP_STRIDE * sizeof(unsigned), st));
+        CK(cudaMemsetAsync(p.hops, 0, ctx->hops_bytes, st));
+        p.ao = ctx->at<float>(ctx->o_ao); p.att_cnt = ctx->at<unsigned>(ctx->o_attcnt);
         p.acc = ctx->at<unsigned long long>(ctx->o_acc);
         CK(cudaMemsetAsync(p.acc, 0, ctx->acc_bytes, st));
         {   // exchange tags: unique per (launch, step, layer, buffer); restart over zeroed buffers before a wrap

@@ -5,16 +5,11 @@
 // until the last one ends (stream_generator.py:860-881).
 //
 // What changes against the single-row kernel:
-//   * GEMV -> skinny GEMM out of the same ring.  The CTA's units (output columns, K = D) are taken 16 at a time:
-//     D[16 units x 8 rows] = W[16 x K] . X^T[K x 8] with warp-level mma (m16n8k8), the 8 warps splitting K.
-//     fp32 parity on tensor cores by 3xTF32 (x = hi + lo, hi = tf32(x); lo.hi + hi.lo + hi.hi in an fp32
-//     accumulator).  Operands come straight from shared memory with ldmatrix: the unit pitch of the stream
-//     (D + 4 floats) puts the 8 row addresses of every 8 x 4-float matrix in 8 different 16-byte bank groups.
-//     (tcgen05 has no shape for this: its smallest tile is 64 rows, and the activations would have to be a
-//     [64 x K] operand per CTA; with 8 rows the step stays HBM-bound, the tensor work is a few % of it.)
-//   * mlp.c_proj stays split along K (the CTA that computed u[:, k] owns row k of W_proj2):
-//     D[16 outputs x 8 rows] += W^T[16 x 8 units] . u^T[8 units x 8 rows], outputs permuted inside 32-column
-//     blocks so the operand loads are conflict-free; the per-CTA partials [8 rows][D] go to the reducer CTAs.
+//   * GEMV -> skinny GEMM out of the same ring, still fp32 FFMA: a warp takes a whole tile (4 units), holds its weights in
+//     registers (128 per lane at D = 1024) and streams the rows of the activation buffer against them
+//     (8 LDS.128 + 128 FFMA per row); one transposing shuffle tree per row, no cross-warp reduction.
+//   * mlp.c_proj stays split along K (the CTA that computed u[:, k] owns row k of W_proj2): thread j accumulates outputs
+//     4j .. 4j+3 of every row in registers; the per-CTA partials [rows][D] go to the reducer CTAs.
 //   * one activation buffer xs[8][D + 4] in shared memory is the B operand of every phase (x -> attention output
 //     -> x1 -> latent); LayerNorm statistics per row by one warp each.
 //   * attention items = (row, head, key range), H * B * nsplit <= grid; the item code is the single-row one.
@@ -28,102 +23,101 @@ namespace gv {
 using namespace megab;
 
 #define NBR GV_BATCH_ROWS
-#define B_PART_FLOATS (2 * MEGA_WARPS * 128)  // [parity][warp][16 units x 8 rows] cross-warp partials of the dot phases
-#define B_US_PITCH 36                         // gelu(fc) values of this CTA: [8 rows][32 units + 4]
-#define B_SCR_BYTES 9728                      // attention scratch (as the single-row kernel) | reducer partials
+#define B_SCR_BYTES 9728  // attention scratch (as the single-row kernel) | reducer partials
 
 // ---------------------------------------------------------------------------------------------
-// warp-level tensor-core primitives (legacy mma path; SASS: LDSM, HMMA.1688.F32.TF32)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                 : "r"(addr)
-                 : "memory");
-}
-__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr) : "memory");
-}
-// x = hi + lo with hi = x rounded to tf32, lo = (x - hi) rounded to tf32
-__device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(__uint_as_float(x)));
-    const float l = __uint_as_float(x) - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(l));
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                         uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-// c += A . B in 3xTF32 (small terms first)
-__device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&bh)[2],
-                                       const uint32_t (&bl)[2]) {
-    mma_tf32(c, al[0], al[1], al[2], al[3], bh[0], bh[1]);
-    mma_tf32(c, ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
-    mma_tf32(c, ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
-}
-
-// ---------------------------------------------------------------------------------------------
-// dot phase (QKV, attn c_proj, FC, logits head): for every unit u < nunits of this CTA and every row r,
-//   dot[u][r] = sum_k W'[k][u] xs[r][k];   epi(u, r, dot, c2, c1)  is called once per (u, r < nb).
-// Units are taken 16 at a time (four ring tiles); warp w covers k in [w D/8, (w+1) D/8); the eight per-warp
-// partial tiles meet in `part` (double-buffered by group parity: one block barrier per group).
-// Every warp reads every tile: the ring's empty barriers count 8 arrivals.
+// dot phase (QKV, attn c_proj, FC, logits head): for every unit u < nunits of this CTA and every row r < nb,
+//   dot[u][r] = sum_k W'[k][u] xs[r][k];   epi(u, r, dot, c2, c1)  is called once per (u, r).
+// A warp takes whole ring tiles (4 units): the tile's weights go to registers once (4 units x D / 32 values per lane),
+// the tile is released, then every row of xs is read from shared memory against them: 8 LDS.128 + 128 FFMA per row and
+// one transposing shuffle tree for the four units -- no cross-warp reduction, fp32 FMA like the single-row kernel.
+// (A first version ran these phases on the warp-level tensor path -- mma.sync m16n8k8, 3xTF32 -- measured on B200 at
+// 2 cycles per mma per SM = 512 MAC/clk/SM; with three products per fp32 MAC and the hi/lo splits that is no faster than
+// the 128 FFMA/clk/SM of the CUDA cores, and it was 4-5x slower in practice: tools/mma_probe.cu)
+// Only the owning warp reads a tile: it arrives on the tile's empty barrier with the full count.
 // ---------------------------------------------------------------------------------------------
 template <int NXV, class Epi>
-__device__ __forceinline__ void dot_phase(const Ring& ring, const Cons& cs, int nunits, const float* xs, float* part, int nb,
-                                          int tid, Epi epi) {
-    constexpr int D = NXV * 128, UF = D + 4, KW = D / MEGA_WARPS, KS = KW / 8;
+__device__ __forceinline__ void dot_phase(const Ring& ring, const Cons& cs, int nunits, const float* xs, int nb, int tid, Epi epi) {
+    constexpr int D = NXV * 128, UF = D + 4;
     const int warp = tid >> 5, lane = tid & 31;
-    const int ngroups = (nunits + 15) >> 4;
     const int ntiles = (nunits + UPT - 1) / UPT;
-    // B operand (rows of xs): lanes 0-7 address rows 0-7 at k + 0, lanes 8-15 at k + 4 (lanes 16-31: ignored, kept valid)
-    const uint32_t b_addr = smem_u32(xs + (lane & 7) * UF + warp * KW + ((lane >> 3) & 1) * 4);
-    for (int g = 0; g < ngroups; ++g) {
-        const int u0 = g << 4;
-        const int nu = min(16, nunits - u0);
-        const int t0 = g << 2, nt = min(4, ntiles - t0);
-        if (lane < nt) tile_ready_wait(ring, cs.gt + (uint32_t)(t0 + lane));
-        __syncwarp();
-        // A operand (units): matrix m = lane / 8: units u0 + (m & 1) * 8 + lane % 8 at k + (m >> 1) * 4; rows past the
-        // end of the phase re-read unit u0 (finite values; their outputs are dropped)
-        int ua = u0 + ((lane >> 3) & 1) * 8 + (lane & 7);
-        if (ua >= nunits) ua = u0;
-        const uint32_t a_addr =
-            smem_u32(slot_ptr(ring, cs.gt + (uint32_t)(ua >> 2)) + (ua & 3) * UF + warp * KW + (lane >> 4) * 4);
-        // epilogue constants of the unit this thread will finish (threads 0..127: unit u0 + tid / 8)
-        float2 cc = make_float2(0.f, 0.f);
-        const int ue = u0 + (tid >> 3);
-        if (tid < 128 && ue < nunits) cc = *reinterpret_cast<const float2*>(slot_ptr(ring, cs.gt + (uint32_t)(ue >> 2)) + (ue & 3) * UF + D);
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = warp; t < ntiles; t += MEGA_WARPS) {
+        long long tw0 = 0;
+        if (cs.wacc != nullptr && tid == 0) tw0 = clock64();  // debug profile: time spent waiting for weight tiles
+        const float* base = tile_wait(ring, Cons{cs.gt, nullptr}, cs.gt + (uint32_t)t, lane);
+        if (cs.wacc != nullptr && tid == 0) *cs.wacc += (unsigned long long)(clock64() - tw0);
+        const int nu = min(UPT, nunits - t * UPT);
+        float4 w[UPT][NXV];
+        float2 cc[UPT];
 #pragma unroll
-        for (int s = 0; s < KS; ++s) {
-            uint32_t a[4], b[2], ah[4], al[4], bh[2], bl[2];
-            ldsm_x4(a_addr + s * 32, a[0], a[1], a[2], a[3]);
-            ldsm_x2(b_addr + s * 32, b[0], b[1]);
+        for (int u = 0; u < UPT; ++u) {
+            const float* col = base + (u < nu ? u : 0) * UF;  // units past the end of the phase: unit 0 again (results dropped)
+            cc[u] = *reinterpret_cast<const float2*>(col + D);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) split_tf32(b[i], bh[i], bl[i]);
-            mma_3x(c, ah, al, bh, bl);
+            for (int i = 0; i < NXV; ++i) w[u][i] = *reinterpret_cast<const float4*>(col + (i * 32 + lane) * 4);
         }
-        // c[0], c[1]: unit lane / 4, rows 2 (lane % 4), +1;  c[2], c[3]: unit lane / 4 + 8
-        float* pw = part + (g & 1) * (MEGA_WARPS * 128) + warp * 128;
-        *reinterpret_cast<float2*>(pw + (lane >> 2) * 8 + 2 * (lane & 3)) = make_float2(c[0], c[1]);
-        *reinterpret_cast<float2*>(pw + ((lane >> 2) + 8) * 8 + 2 * (lane & 3)) = make_float2(c[2], c[3]);
-        __syncwarp();
-        if (lane < nt) mbar_arrive(&ring.empty[(cs.gt + (uint32_t)(t0 + lane)) % NSLOT]);
-        bar_sync(1, MEGA_CONSUMERS);
-        if (tid < 128) {
-            const int ul = tid >> 3, r = tid & 7;
-            if (ul < nu && r < nb) {
-                const float* pr = part + (g & 1) * (MEGA_WARPS * 128) + ul * 8 + r;
-                float s = 0.0f;
+        tile_release(ring, cs.gt + (uint32_t)t, lane, (uint32_t)MEGA_WARPS);
+        // two rows per iteration (independent accumulator sets, eight LDS.128 in flight): the tile is handled by ONE warp, so
+        // the instruction-level parallelism has to come from inside the warp
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+        const int q = lane >> 3;
+        const float2 c = up16 ? (up8 ? cc[3] : cc[2]) : (up8 ? cc[1] : cc[0]);
+        for (int r0 = 0; r0 < nb; r0 += 2) {
+            const float* xa = xs + r0 * UF + lane * 4;
+            const float* xb = xa + UF;  // row r0 + 1 (always inside xs; dropped when r0 + 1 == nb)
+            float a0[UPT], a1[UPT], b0[UPT], b1[UPT];
 #pragma unroll
-                for (int w = 0; w < MEGA_WARPS; ++w) s += pr[w * 128];
-                epi(u0 + ul, r, s, cc.x, cc.y);
+            for (int u = 0; u < UPT; ++u) a0[u] = a1[u] = b0[u] = b1[u] = 0.0f;
+            constexpr int HB = NXV >= 2 ? NXV / 2 : 1;
+#pragma unroll
+            for (int h = 0; h < NXV / HB; ++h) {
+                float4 va[HB], vb[HB];
+#pragma unroll
+                for (int i = 0; i < HB; ++i) {
+                    va[i] = *reinterpret_cast<const float4*>(xa + (h * HB + i) * 128);
+                    vb[i] = *reinterpret_cast<const float4*>(xb + (h * HB + i) * 128);
+                }
+#pragma unroll
+                for (int i = 0; i < HB; ++i) {
+#pragma unroll
+                    for (int u = 0; u < UPT; ++u) {
+                        const float4 wv = w[u][h * HB + i];
+                        a0[u] = fmaf(wv.x, va[i].x, a0[u]);
+                        a1[u] = fmaf(wv.y, va[i].y, a1[u]);
+                        b0[u] = fmaf(wv.x, vb[i].x, b0[u]);
+                        b1[u] = fmaf(wv.y, vb[i].y, b1[u]);
+                        a0[u] = fmaf(wv.z, va[i].z, a0[u]);
+                        a1[u] = fmaf(wv.w, va[i].w, a1[u]);
+                        b0[u] = fmaf(wv.z, vb[i].z, b0[u]);
+                        b1[u] = fmaf(wv.w, vb[i].w, b1[u]);
+                    }
+                }
+            }
+            // transposing butterflies (both rows interleaved): lanes [8q, 8q+8) end up reducing unit q
+            float ta[UPT], tb[UPT];
+#pragma unroll
+            for (int u = 0; u < UPT; ++u) {
+                ta[u] = a0[u] + a1[u];
+                tb[u] = b0[u] + b1[u];
+            }
+            const float ka0 = up16 ? ta[2] : ta[0], sa0 = up16 ? ta[0] : ta[2];
+            const float ka1 = up16 ? ta[3] : ta[1], sa1 = up16 ? ta[1] : ta[3];
+            const float kb0 = up16 ? tb[2] : tb[0], sb0 = up16 ? tb[0] : tb[2];
+            const float kb1 = up16 ? tb[3] : tb[1], sb1 = up16 ? tb[1] : tb[3];
+            const float ha0 = ka0 + __shfl_xor_sync(0xffffffffu, sa0, 16);
+            const float ha1 = ka1 + __shfl_xor_sync(0xffffffffu, sa1, 16);
+            const float hb0 = kb0 + __shfl_xor_sync(0xffffffffu, sb0, 16);
+            const float hb1 = kb1 + __shfl_xor_sync(0xffffffffu, sb1, 16);
+            float va_ = (up8 ? ha1 : ha0) + __shfl_xor_sync(0xffffffffu, up8 ? ha0 : ha1, 8);
+            float vb_ = (up8 ? hb1 : hb0) + __shfl_xor_sync(0xffffffffu, up8 ? hb0 : hb1, 8);
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                va_ += __shfl_xor_sync(0xffffffffu, va_, o);
+                vb_ += __shfl_xor_sync(0xffffffffu, vb_, o);
+            }
+            if ((lane & 7) == 0 && q < nu) {
+                epi(t * UPT + q, r0, va_, c.x, c.y);
+                if (r0 + 1 < nb) epi(t * UPT + q, r0 + 1, vb_, c.x, c.y);
             }
         }
     }
@@ -131,71 +125,73 @@ __device__ __forceinline__ void dot_phase(const Ring& ring, const Cons& cs, int 
 
 // ---------------------------------------------------------------------------------------------
 // mlp.c_proj split along K: unit k = row k of W_proj2 (owned by the CTA that computed u[:, k]).
-//   part[r][n] = sum_k us[r][k] W[k][n]    for all D outputs n, rows r
-// as D[16 outputs x 8 rows] += A[16 outputs x 8 units] . B[8 units x 8 rows]: A element (output i, unit k) is
-// slot(k)[col(i)] with col(i) = c0 + i % 4 + 16 (i / 4 % 2) + 4 (i / 8) inside a 32-column block, so the 32 lanes of
-// one operand load (unit = lane % 4, output = lane / 4) hit 32 different banks (unit pitch = D + 4 floats).
-// Warp w owns m-tiles w NXV .. w NXV + NXV - 1 (16 outputs each).  Two ring tiles (8 units) per k-step.
+//   part[r][n] = sum_k usT[k][r] W[k][n]    for all D outputs n, rows r < nb
+// Thread j owns outputs 4j .. 4j+3 for every row (accumulators in registers); per unit one LDS.128 of the row of
+// W_proj2 and two broadcast LDS.128 of the unit's 8 row values.  Every warp reads every tile (one arrival each).
 // Results go straight to the exchange buffer pp[cta][n / 8][row][n % 8] (tagged).
 // ---------------------------------------------------------------------------------------------
 template <int NXV>
-__device__ __forceinline__ void outer_phase(const Ring& ring, const Cons& cs, int nunits, const float* us, int nb, int tid,
+__device__ __forceinline__ void outer_phase(const Ring& ring, const Cons& cs, int nunits, const float* usT, int nb, int tid,
                                             float* pp_cta, uint32_t tag) {
     constexpr int D = NXV * 128, UF = D + 4;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, j = lane & 3;
+    const int lane = tid & 31;
+    const bool valid = 4 * tid < D;
     const int ntiles = (nunits + UPT - 1) / UPT;
-    const int nks = (nunits + 7) >> 3;
-    float acc[NXV][4];
+    float4 acc[NBR];
 #pragma unroll
-    for (int m = 0; m < NXV; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.0f;
-    // output columns of this lane in m-tile T: rows g and g + 8 of the tile
-    const int cg0 = (g & 3) + 16 * (g >> 2);  // col(g) - c0;  col(g + 8) = col(g) + 4
-    for (int ks = 0; ks < nks; ++ks) {
-        const int t0 = 2 * ks, nt = min(2, ntiles - t0);
-        if (lane < nt) tile_ready_wait(ring, cs.gt + (uint32_t)(t0 + lane));
-        __syncwarp();
-        // B operand: b0 = us[row g][8 ks + j], b1 = us[row g][8 ks + j + 4]   (zero beyond nunits / nb)
-        uint32_t bh[2], bl[2];
-        split_tf32(__float_as_uint(us[g * B_US_PITCH + 8 * ks + j]), bh[0], bl[0]);
-        split_tf32(__float_as_uint(us[g * B_US_PITCH + 8 * ks + j + 4]), bh[1], bl[1]);
-        // A operand rows: units 8 ks + j (tile t0, row j) and 8 ks + j + 4 (tile t0 + 1, row j); units past the end
-        // re-read unit 8 ks (finite weights; multiplied by us = 0)
-        const int k0 = 8 * ks + j, k1 = k0 + 4;
-        const float* wz = slot_ptr(ring, cs.gt + (uint32_t)t0);
-        const float* w0 = (k0 < nunits) ? wz + j * UF : wz;
-        const float* w1 = (k1 < nunits) ? slot_ptr(ring, cs.gt + (uint32_t)(t0 + 1)) + j * UF : wz;
+    for (int r = 0; r < NBR; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < ntiles; ++t) {
+        long long tw0 = 0;
+        if (cs.wacc != nullptr && tid == 0) tw0 = clock64();
+        const float* base = tile_wait(ring, Cons{cs.gt, nullptr}, cs.gt + (uint32_t)t, lane);
+        if (cs.wacc != nullptr && tid == 0) *cs.wacc += (unsigned long long)(clock64() - tw0);
+        if (valid) {
+            float4 wv[UPT], ua[UPT], ub[UPT];
 #pragma unroll
-        for (int m = 0; m < NXV; ++m) {
-            const int T = warp * NXV + m;
-            const int c0 = 32 * (T >> 1) + 8 * (T & 1) + cg0;
-            uint32_t a[4], ah[4], al[4];
-            a[0] = __float_as_uint(w0[c0]);
-            a[1] = __float_as_uint(w0[c0 + 4]);
-            a[2] = __float_as_uint(w1[c0]);
-            a[3] = __float_as_uint(w1[c0 + 4]);
+            for (int u = 0; u < UPT; ++u) {  // the tile's four weight rows and their row values: twelve LDS.128 in flight
+                const int k = min(t * UPT + u, nunits - 1);  // (units past the end: values unused)
+                wv[u] = *reinterpret_cast<const float4*>(base + (t * UPT + u < nunits ? u : 0) * UF + 4 * tid);
+                ua[u] = *reinterpret_cast<const float4*>(usT + k * NBR);
+                ub[u] = *reinterpret_cast<const float4*>(usT + k * NBR + 4);
+            }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
-            mma_3x(acc[m], ah, al, bh, bl);
+            for (int u = 0; u < UPT; ++u) {
+                if (t * UPT + u < nunits) {
+                    const float ur[NBR] = {ua[u].x, ua[u].y, ua[u].z, ua[u].w, ub[u].x, ub[u].y, ub[u].z, ub[u].w};
+#pragma unroll
+                    for (int r = 0; r < NBR; ++r) {
+                        if (r < nb) {
+                            acc[r].x = fmaf(ur[r], wv[u].x, acc[r].x);
+                            acc[r].y = fmaf(ur[r], wv[u].y, acc[r].y);
+                            acc[r].z = fmaf(ur[r], wv[u].z, acc[r].z);
+                            acc[r].w = fmaf(ur[r], wv[u].w, acc[r].w);
+                        }
+                    }
+                }
+            }
         }
-        __syncwarp();
-        if (lane < nt) mbar_arrive(&ring.empty[(cs.gt + (uint32_t)(t0 + lane)) % NSLOT]);
+        tile_release(ring, cs.gt + (uint32_t)t, lane);
     }
-    // acc[m][0], [1]: output col(g), rows 2j, 2j+1;  acc[m][2], [3]: output col(g) + 4
+    if (cs.wacc != nullptr && tid == 0) cs.wacc[1] -= (unsigned long long)clock64();  // debug profile [14]: stores
+    if (valid) {
+        const int n = 4 * tid;
 #pragma unroll
-    for (int m = 0; m < NXV; ++m) {
-        const int T = warp * NXV + m;
-        const int n0 = 32 * (T >> 1) + 8 * (T & 1) + cg0;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int n = n0 + 4 * h;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int r = 2 * j + q;
-                if (r < nb) st_tagged(pp_cta, ((n >> 3) * NBR + r) * 8 + (n & 7), acc[m][2 * h + q], tag);
+        for (int r = 0; r < NBR; ++r) {
+            if (r < nb) {
+                const int idx = ((n >> 3) * NBR + r) * 8 + (n & 7);
+                st_tagged2(pp_cta, idx, acc[r].x, acc[r].y, tag);
+                st_tagged2(pp_cta, idx + 2, acc[r].z, acc[r].w, tag);
             }
         }
     }
+    if (cs.wacc != nullptr && tid == 0) cs.wacc[1] += (unsigned long long)clock64();
+}
+
+// activation rows [8][D + 4]; the sampling sort keys (16 KB) alias them (and the scratch region that follows, dead then)
+__host__ __device__ inline size_t batch_xs_bytes(int D) {
+    const size_t rows = (size_t)NBR * (D + 4) * sizeof(float);
+    const size_t keys = (size_t)GV_SORT_N * 8 > B_SCR_BYTES ? (size_t)GV_SORT_N * 8 - B_SCR_BYTES : 0;
+    return rows > keys ? rows : (keys + 15) / 16 * 16;
 }
 
 // rows 0 .. nb-1 of a tagged [rows][D] exchange buffer -> xs (thread t owns elements 4t .. 4t+3 of every row); all loads
@@ -320,15 +316,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
     off = (off + 127) & ~size_t(127);
     float* xs = reinterpret_cast<float*>(smem_raw + off);  // [8][D + 4] activation rows: the B operand of every phase
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + off);  // sampling sort keys (xs is dead then)
-    off += (size_t)NBR * UF * sizeof(float);
-    float* part = reinterpret_cast<float*>(smem_raw + off);
-    off += (size_t)B_PART_FLOATS * sizeof(float);
+    off += batch_xs_bytes(D);
     float* att_sc = reinterpret_cast<float*>(smem_raw + off);         // attention: per-warp (max, sum) + q staging
     float* att_op = reinterpret_cast<float*>(smem_raw + off + 1280);  // attention: [8][hd] per-warp PV partials
-    float* red4 = reinterpret_cast<float*>(smem_raw + off);           // reducer CTAs: [4][64] partial sums
+    float* red4 = reinterpret_cast<float*>(smem_raw + off);           // reducer CTAs: [8 warps][64] partial sums
     off += B_SCR_BYTES;
-    float* us = reinterpret_cast<float*>(smem_raw + off);  // [8][B_US_PITCH] gelu(fc) of this CTA's units
-    off += (size_t)NBR * B_US_PITCH * sizeof(float);
+    float* us = reinterpret_cast<float*>(smem_raw + off);  // [32 units][8 rows] gelu(fc) of this CTA's units (zero past nb)
+    off += (size_t)32 * NBR * sizeof(float);
     float* stats = reinterpret_cast<float*>(smem_raw + off);  // [8][2] mean, rstd of the LayerNorm folded into the phase
     off += 2 * NBR * sizeof(float);
     float* resid = reinterpret_cast<float*>(smem_raw + off);  // [8 rows][8] block input at this CTA's attn c_proj columns
@@ -350,6 +344,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
     off += NBR * sizeof(int);
     int* fin = reinterpret_cast<int*>(smem_raw + off);  // [8] row finished
     off += NBR * sizeof(int);
+    unsigned long long* prof = reinterpret_cast<unsigned long long*>(smem_raw + off);  // [16] debug: cycles per phase (thread 0)
+    off += 16 * sizeof(unsigned long long);
     unsigned char* seen = smem_raw + off;  // [Vpad] ids present in the row this CTA samples (repetition penalty)
 
     if (tid_all == 0) {
@@ -368,7 +364,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
     if (cta < NB)
         for (int i = tid_all; i < p.Vpad; i += MEGA_THREADS) seen[i] = p.seen[(size_t)cta * p.Vpad + i];
     for (int i = tid_all; i < NBR * UF; i += MEGA_THREADS) xs[i] = 0.0f;
-    for (int i = tid_all; i < NBR * B_US_PITCH; i += MEGA_THREADS) us[i] = 0.0f;
+    for (int i = tid_all; i < 32 * NBR; i += MEGA_THREADS) us[i] = 0.0f;
     if (tid_all < NBR) {
         ltok[tid_all] = tid_all < NB ? (int)st->last_tok[tid_all] : 0;
         fin[tid_all] = tid_all < NB ? st->finished[tid_all] : 1;
@@ -443,7 +439,23 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
     const float* mel_pos = p.blob + p.mel_pos_off;
     unsigned* const hc = p.hops;
     const unsigned near = p.hop_near >= 0 ? (unsigned)p.hop_near : (unsigned)max(G / 37, 1);
-    unsigned lc = 0, t_ao = 0, t_lg = 0;
+    const unsigned settle = (unsigned)p.hop_settle_ns;
+    unsigned lc = 0, t_ao = 0, t_lg = 0, t_cnt = 0;
+    // debug phase profile (genvc_debug_trace): thread 0 accumulates the cycles between consecutive marks
+    const bool profiling = p.trace != nullptr && tid == 0;
+    long long pclk = 0;
+    if (profiling) {
+        for (int k = 0; k < 16; ++k) prof[k] = 0ull;
+        pclk = clock64();
+        cs.wacc = prof + 12;  // [12] tile waits of the dot phases, [13] of mlp.c_proj
+    }
+    auto mark = [&](int k) {
+        if (profiling) {
+            const long long c = clock64();
+            prof[k] += (unsigned long long)(c - pclk);
+            pclk = c;
+        }
+    };
     const size_t xq_row = 2 * (size_t)3 * D, x_row = 2 * (size_t)D, lg_row = 2 * (size_t)p.Vpad;
 
     for (int i = 0; i < p.n_steps; ++i) {
@@ -457,7 +469,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
             const int chunk = att_chunk_b(S, nsplit0);
             const int nsplit = (S + chunk - 1) / chunk;
             const int n_items = NB * H * nsplit;
-            const unsigned near_ao = p.hop_near_ao >= 0 ? (unsigned)p.hop_near_ao : (unsigned)min(max(n_items / 3, 1), 4);
+            const unsigned near_ao = p.hop_near_ao >= 0 ? (unsigned)p.hop_near_ao : (unsigned)min(max(NB * H / 3, 1), 4);
             for (int l = 0; l < p.L; ++l) {
                 float* kc = p.kv + ((size_t)l * 2 + 0) * p.kv_layer_stride;
                 float* vc = p.kv + ((size_t)l * 2 + 1) * p.kv_layer_stride;
@@ -472,152 +484,199 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
                         }
                     }
                 } else {
-                    hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, 0u, nullptr, near);
+                    hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, settle, nullptr, near);
                     load_rows<D>(p.x2, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, xs, NB, tid);
                 }
                 bar_sync(1, MEGA_CONSUMERS);
+                mark(0);  // x2 hop + load
                 // ---- QKV: [q|k|v] = LN1(x) . W_attn + b  (LN folded into the packed weights: statistics enter in the epilogue) ----
                 row_stats<NXV>(xs, stats, NB, warp, lane);
                 if (tid < NBR * 8) {  // block input at this CTA's attn c_proj columns (residual of the PROJ epilogue)
                     const int r = tid >> 3, u = tid & 7;
                     if (r < NB && u < nun[PH_PROJ]) resid[tid] = xs[r * UF + ubeg[PH_PROJ] + u];
                 }
-                dot_phase<NXV>(ring, cs, nun[PH_QKV], xs, part, NB, tid, [&](int u, int r, float dot, float c2, float c1) {
+                bar_sync(1, MEGA_CONSUMERS);  // statistics visible to the epilogues
+                dot_phase<NXV>(ring, cs, nun[PH_QKV], xs, NB, tid, [&](int u, int r, float dot, float c2, float c1) {
                     const float mean = stats[2 * r], rstd = stats[2 * r + 1];
                     st_tagged(p.xq + r * xq_row, ubeg[PH_QKV] + u, fmaf(rstd, fmaf(-mean, c1, dot), c2), tg + TG_XQ);
                 });
                 cs.gt += (uint32_t)ntl[PH_QKV];
-                // ---- ATT: (row, head, key-range) items on the first n_items CTAs ----
+                mark(1);  // stats + QKV
+                // ---- ATT: (row, head, key-range) items on the first n_items CTAs.  The CTA of range 0 merges the nsplit
+                // partials of its (row, head) in split order (the other ranges bump a per-(row, head) counter, one thread
+                // of the merger polls it, the tags validate the data) and publishes the normalised output segment: every
+                // CTA then loads B x D finished values instead of B x nsplit x D partials (measured: the per-CTA merge
+                // of all rows was 10 us per layer at B = 8) ----
                 if (cta < n_items) {
                     const int rh = cta / nsplit, sp = cta % nsplit;
                     const int r = rh / H, h = rh % H;
                     const int j0 = sp * chunk, j1 = min(S, j0 + chunk);
                     float* kh = kc + ((size_t)r * H + h) * p.S_max * HD;
                     float* vh = vc + ((size_t)r * H + h) * p.S_max * HD;
+                    if (nsplit == 1) {
+#define GV_ATT_CASE(hd)                                                                                                    \
+    case hd:                                                                                                               \
+        att_item<hd, false, true>(kh, vh, p.xq + r * xq_row, D, h, j0, j1, S, tg + TG_XQ, att_sc, att_op, tid, p.ao + r * x_row, \
+                                  nullptr, h, tg + TG_AO, tmask, nullptr);                                                 \
+        break;
+                        switch (HD) {
+                            GV_ATT_CASE(32) GV_ATT_CASE(64) GV_ATT_CASE(128) GV_ATT_CASE(256)
+                            default: break;
+                        }
+#undef GV_ATT_CASE
+                        hop_arrive(hc + HC_AO * GV_HOP_STRIDE, tid);
+                    } else {
 #define GV_ATT_CASE(hd)                                                                                                  \
     case hd:                                                                                                             \
         att_item<hd, false>(kh, vh, p.xq + r * xq_row, D, h, j0, j1, S, tg + TG_XQ, att_sc, att_op, tid, p.att_o, p.att_ml, \
                             cta, tg + TG_AO, tmask, nullptr);                                                            \
         break;
-                    switch (HD) {
-                        GV_ATT_CASE(32) GV_ATT_CASE(64) GV_ATT_CASE(128) GV_ATT_CASE(256)
-                        default: break;
-                    }
-#undef GV_ATT_CASE
-                    hop_arrive(hc + HC_AO * GV_HOP_STRIDE, tid);
-                }
-                t_ao += (unsigned)n_items;
-                // ---- PROJ: merge the items' partials -> attention output rows (xs); x1 = x + o . W_proj + b ----
-                hop_wait(hc + HC_AO * GV_HOP_STRIDE, t_ao, tid, tmask, 0u, nullptr, near_ao);
-                if (xvalid) {
-                    const int h = (4 * tid) / HD, d = (4 * tid) % HD;
-                    const uint32_t tga = tg + TG_AO;
-                    for (int r = 0; r < NB; ++r) {
-                        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, M = -INFINITY, den = 0.0f;
-                        for (int s0 = 0; s0 < nsplit; s0 += 4) {  // loads of four splits in flight, merged in split order
-                            uint4 a[4], b[4], c[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (s0 + q < nsplit) {
-                                    const int it = (r * H + h) * nsplit + s0 + q;
-                                    a[q] = ld_x16(p.att_ml + 2 * (size_t)(it * 2));
-                                    b[q] = ld_x16(p.att_o + 2 * (size_t)(it * HD + d));
-                                    c[q] = ld_x16(p.att_o + 2 * (size_t)(it * HD + d + 2));
-                                }
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (s0 + q < nsplit) {
-                                    const int it = (r * H + h) * nsplit + s0 + q;
-                                    uint32_t spins = 0;
-                                    while (!(tags_ok(a[q], tga, tmask) && tags_ok(b[q], tga, tmask) && tags_ok(c[q], tga, tmask))) {
-                                        if (++spins > MEGA_SPIN_LIMIT) __trap();
-                                        a[q] = ld_x16(p.att_ml + 2 * (size_t)(it * 2));
-                                        b[q] = ld_x16(p.att_o + 2 * (size_t)(it * HD + d));
-                                        c[q] = ld_x16(p.att_o + 2 * (size_t)(it * HD + d + 2));
-                                    }
-                                    const float mq = __uint_as_float(a[q].x), lq = __uint_as_float(a[q].z);
-                                    const float Mn = fmaxf(M, mq);
-                                    const float c_old = expf(M - Mn);  // first split: exp(-inf) = 0
-                                    const float c_new = expf(mq - Mn);
-                                    den = den * c_old + lq * c_new;
-                                    o0 = o0 * c_old + __uint_as_float(b[q].x) * c_new;
-                                    o1 = o1 * c_old + __uint_as_float(b[q].z) * c_new;
-                                    o2 = o2 * c_old + __uint_as_float(c[q].x) * c_new;
-                                    o3 = o3 * c_old + __uint_as_float(c[q].z) * c_new;
-                                    M = Mn;
-                                }
-                            }
+                        switch (HD) {
+                            GV_ATT_CASE(32) GV_ATT_CASE(64) GV_ATT_CASE(128) GV_ATT_CASE(256)
+                            default: break;
                         }
-                        *reinterpret_cast<float4*>(xs + r * UF + 4 * tid) = make_float4(o0 / den, o1 / den, o2 / den, o3 / den);
+#undef GV_ATT_CASE
+                        if (sp != 0) {
+                            // arrival on the (row, head) counter: a hint for the merging CTA (the tags validate the data)
+                            if (tid == 0) red_relaxed_add(p.att_cnt + (size_t)rh * GV_ATTCNT_STRIDE, 1u);
+                        } else {  // the CTA of split 0 merges the (row, head)
+                            if (tid == 0) {  // one poller on the counter line; nobody polls lines that are still being written
+                                const unsigned* cnt = p.att_cnt + (size_t)rh * GV_ATTCNT_STRIDE;
+                                uint32_t spins = 0;
+                                while (ld_relaxed_u32(cnt) < t_cnt + (unsigned)(nsplit - 1)) {
+                                    if (++spins > MEGA_SPIN_LIMIT) __trap();
+                                }
+                            }
+                            bar_sync(1, MEGA_CONSUMERS);
+                            if (tid < HD) {
+                                const uint32_t tga = tg + TG_AO;
+                                float M = -INFINITY, den = 0.0f, o = 0.0f;
+                                for (int s0 = 0; s0 < nsplit; s0 += 4) {
+                                    uint4 a[4];
+                                    uint2 b[4];
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        if (s0 + q < nsplit) {
+                                            const int it = rh * nsplit + s0 + q;
+                                            a[q] = ld_x16(p.att_ml + 2 * (size_t)(it * 2));
+                                            b[q] = ld_x8(p.att_o + 2 * (size_t)(it * HD + tid));
+                                        }
+                                    }
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        if (s0 + q < nsplit) {
+                                            const int it = rh * nsplit + s0 + q;
+                                            uint32_t spins = 0;
+                                            while (!(tags_ok(a[q], tga, tmask) && b[q].y == tga)) {
+                                                if (++spins > MEGA_SPIN_LIMIT) __trap();
+                                                a[q] = ld_x16(p.att_ml + 2 * (size_t)(it * 2));
+                                                b[q] = ld_x8(p.att_o + 2 * (size_t)(it * HD + tid));
+                                            }
+                                            const float mq = __uint_as_float(a[q].x), lq = __uint_as_float(a[q].z);
+                                            const float Mn = fmaxf(M, mq);
+                                            const float c_old = expf(M - Mn);  // first split: exp(-inf) = 0
+                                            const float c_new = expf(mq - Mn);
+                                            den = den * c_old + lq * c_new;
+                                            o = o * c_old + __uint_as_float(b[q].x) * c_new;
+                                            M = Mn;
+                                        }
+                                    }
+                                }
+                                st_tagged(p.ao + r * x_row, h * HD + tid, o / den, tga);
+                            }
+                            hop_arrive(hc + HC_AO * GV_HOP_STRIDE, tid);
+                        }
                     }
                 }
+                if (nsplit > 1) t_cnt += (unsigned)(nsplit - 1);  // arrivals per (row, head) counter and layer
+                t_ao += (unsigned)(NB * H);
+                mark(2);  // attention item
+                // ---- PROJ: attention output rows -> xs; x1 = x + o . W_proj + b ----
+                hop_wait(hc + HC_AO * GV_HOP_STRIDE, t_ao, tid, tmask, settle, nullptr, near_ao);
+                mark(3);  // AO hop
+                load_rows<D>(p.ao, tg + TG_AO, xs, NB, tid);
                 bar_sync(1, MEGA_CONSUMERS);
-                dot_phase<NXV>(ring, cs, nun[PH_PROJ], xs, part, NB, tid, [&](int u, int r, float dot, float c2, float) {
+                mark(4);  // merge
+                dot_phase<NXV>(ring, cs, nun[PH_PROJ], xs, NB, tid, [&](int u, int r, float dot, float c2, float) {
                     st_tagged(p.x1 + r * x_row, ubeg[PH_PROJ] + u, resid[r * 8 + u] + (dot + c2), tg + TG_X1);
                 });
                 cs.gt += (uint32_t)ntl[PH_PROJ];
                 hop_arrive(hc + HC_X1 * GV_HOP_STRIDE, tid);
+                mark(5);  // PROJ
                 // ---- FC + P2: u = gelu_new(LN2(x1) . W_fc + b) (kept in this CTA) -> partial of u . W_proj2 ----
-                hop_wait(hc + HC_X1 * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, 0u, nullptr, near);
+                hop_wait(hc + HC_X1 * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, nullptr, near);
                 load_rows<D>(p.x1, tg + TG_X1, xs, NB, tid);
                 bar_sync(1, MEGA_CONSUMERS);
+                mark(6);  // x1 hop + load
                 row_stats<NXV>(xs, stats, NB, warp, lane);
-                dot_phase<NXV>(ring, cs, nun[PH_FC], xs, part, NB, tid, [&](int u, int r, float dot, float c2, float c1) {
+                bar_sync(1, MEGA_CONSUMERS);  // statistics visible to the epilogues
+                dot_phase<NXV>(ring, cs, nun[PH_FC], xs, NB, tid, [&](int u, int r, float dot, float c2, float c1) {
                     const float mean = stats[2 * r], rstd = stats[2 * r + 1];
-                    us[r * B_US_PITCH + u] = gelu_new(fmaf(rstd, fmaf(-mean, c1, dot), c2));
+                    us[u * NBR + r] = gelu_new(fmaf(rstd, fmaf(-mean, c1, dot), c2));
                 });
                 cs.gt += (uint32_t)ntl[PH_FC];
+                long long tb0 = 0;
+                if (profiling) tb0 = clock64();
                 bar_sync(1, MEGA_CONSUMERS);
+                if (profiling) prof[15] += (unsigned long long)(clock64() - tb0);  // [15]: barrier after FC (thread 0's wait)
+                mark(7);  // stats + FC
+                if (profiling) cs.wacc = prof + 13;
                 outer_phase<NXV>(ring, cs, nun[PH_P2], us, NB, tid, p.pp + 2 * (size_t)cta * NBR * D, tg + TG_PP);
+                if (profiling) cs.wacc = prof + 12;
                 cs.gt += (uint32_t)ntl[PH_P2];
                 hop_arrive(hc + HC_PP * GV_HOP_STRIDE, tid);
+                mark(8);  // P2
                 // ---- RED: x2 = x1 + b + sum over CTAs of the partials (8 outputs x 8 rows per reducer CTA) ----
                 if (cta < n_red) {
-                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, 0u, nullptr, near);
+                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, nullptr, near);
                     const uint32_t tgp = tg + TG_PP;
-                    const int o = tid & 63, q = tid >> 6;  // output (row o / 8, column 8 cta + o % 8); sources q, q + 4, ...
-                    float acc = 0.0f;
-                    if ((o >> 3) < NB) {
-                        const float* src = p.pp + 2 * ((size_t)cta * 64 + o);
+                    // thread: output pair o2 = lane (row o2 / 4, columns 8 cta + 2 (o2 % 4), +1), sources warp, warp + 8, ...
+                    const int o2 = lane, q = warp;
+                    float acc0 = 0.0f, acc1 = 0.0f;
+                    if ((o2 >> 2) < NB) {
+                        const float* src = p.pp + 2 * ((size_t)cta * 64 + 2 * o2);
                         const size_t sstride = 2 * (size_t)NBR * D;
-                        for (int s0 = q; s0 < G; s0 += 32) {
-                            uint2 v[8];
+                        for (int s0 = q; s0 < G; s0 += 80) {  // ten 16-byte loads in flight
+                            uint4 v[10];
 #pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                if (s0 + 4 * k < G) v[k] = ld_x8(src + (size_t)(s0 + 4 * k) * sstride);
+                            for (int k = 0; k < 10; ++k)
+                                if (s0 + 8 * k < G) v[k] = ld_x16(src + (size_t)(s0 + 8 * k) * sstride);
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                if (s0 + 4 * k < G) {
+                            for (int k = 0; k < 10; ++k) {
+                                if (s0 + 8 * k < G) {
                                     uint32_t spins = 0;
-                                    while (v[k].y != tgp) {
+                                    while (!tags_ok(v[k], tgp, tmask)) {
                                         if (++spins > MEGA_SPIN_LIMIT) __trap();
-                                        v[k] = ld_x8(src + (size_t)(s0 + 4 * k) * sstride);
+                                        v[k] = ld_x16(src + (size_t)(s0 + 8 * k) * sstride);
                                     }
-                                    acc += __uint_as_float(v[k].x);
+                                    acc0 += __uint_as_float(v[k].x);
+                                    acc1 += __uint_as_float(v[k].z);
                                 }
                             }
                         }
                     }
-                    red4[q * 64 + o] = acc;
+                    *reinterpret_cast<float2*>(red4 + q * 64 + 2 * o2) = make_float2(acc0, acc1);
                     bar_sync(1, MEGA_CONSUMERS);
                     if (tid < 64 && (tid >> 3) < NB) {
                         const int r = tid >> 3, col = cta * 8 + (tid & 7);
                         const float b2 = __ldg(p.blob + p.proj2_b_off + (long long)l * p.layer_stride + col);
-                        const float s = (red4[tid] + red4[64 + tid]) + (red4[128 + tid] + red4[192 + tid]);
+                        float s = 0.0f;
+#pragma unroll
+                        for (int w = 0; w < MEGA_WARPS; ++w) s += red4[w * 64 + tid];
                         st_tagged(p.x2 + r * x_row, col, (xs[r * UF + col] + b2) + s, tg + TG_X2);
                     }
                     hop_arrive(hc + HC_X2 * GV_HOP_STRIDE, tid);
+                    mark(9);  // reduce (reducer CTAs)
                 }
                 lc += 1u;
             }
             // ---- HEAD: ln_f -> final_norm -> latent rows z ; logits = z . mel_head^T + b ----
             {
                 const uint32_t tg = tbase + (uint32_t)GV_TAGS_PER_LAYER * (uint32_t)p.L;
-                hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, 0u, nullptr, near);
+                hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, settle, nullptr, near);
                 load_rows<D>(p.x2, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, xs, NB, tid);
                 bar_sync(1, MEGA_CONSUMERS);
-                const float* lnp = tile_wait(ring, cs, cs.gt, lane);  // all warps read the parameter tile
+                const float* lnp = tile_wait(ring, Cons{cs.gt, nullptr}, cs.gt, lane);  // all warps read the parameter tile
                 row_layernorm2<NXV>(xs, lnp, NB, warp, lane);
                 bar_sync(1, MEGA_CONSUMERS);
                 if (warp == 0) tile_release(ring, cs.gt, lane, (uint32_t)MEGA_WARPS);
@@ -625,14 +684,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
                 if (cta < NB && xvalid)  // the latent of the row this CTA samples
                     *reinterpret_cast<float4*>(p.latents_out + ((size_t)i * NB + cta) * D + 4 * tid) =
                         *reinterpret_cast<const float4*>(xs + cta * UF + 4 * tid);
-                dot_phase<NXV>(ring, cs, nun[PH_HEAD], xs, part, NB, tid, [&](int u, int r, float dot, float c2, float) {
+                dot_phase<NXV>(ring, cs, nun[PH_HEAD], xs, NB, tid, [&](int u, int r, float dot, float c2, float) {
                     st_tagged(p.lg + r * lg_row, ubeg[PH_HEAD] + u, dot + c2, tg);
                 });
                 cs.gt += (uint32_t)ntl[PH_HEAD];
                 hop_arrive(hc + HC_LG * GV_HOP_STRIDE, tid);
                 t_lg += (unsigned)G;
                 if (cta < NB) {
-                    hop_wait(hc + HC_LG * GV_HOP_STRIDE, t_lg, tid, tmask, 0u, nullptr, near);
+                    hop_wait(hc + HC_LG * GV_HOP_STRIDE, t_lg, tid, tmask, settle, nullptr, near);
                     const float* lgr = p.lg + cta * lg_row;
                     for (int e = 2 * tid; e < p.V; e += 2 * MEGA_CONSUMERS) {
                         if (e + 1 < p.V) {
@@ -653,6 +712,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
                     ldcg4(p.pend_latent + (size_t)cta * D + 4 * tid);
         }
         bar_sync(1, MEGA_CONSUMERS);  // slog complete; xs (aliased by the sort keys) is dead
+        mark(10);  // head (+ logits hop on the sampling CTAs)
         // ------------- sample + emit: row r by CTA r -------------
         if (cta < NB) {
             int tok = sample_token([&](int e) { return slog[e]; }, seen, scfg,
@@ -681,6 +741,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
         n += 1;
         emitted += 1;
         bar_sync(1, MEGA_CONSUMERS);  // ltok / fin / seen visible; slog / keys free
+        mark(11);  // sampling + token exchange
         int all_fin = 1;
         for (int r = 0; r < NB; ++r) all_fin &= fin[r];
         if (all_fin || n >= p.max_total) {
@@ -688,6 +749,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
             break;
         }
     }
+    if (profiling)
+        for (int k = 0; k < 16; ++k) p.trace[(size_t)cta * 16 + k] = prof[k];
     // tell the producer to stop (it may be blocked on a full ring or still have copies in flight)
     if (tid == 0) {
         ctl[1] = (int)cs.gt;
@@ -719,15 +782,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
 size_t batch_smem_bytes(int D, int Vpad) {
     size_t off = (size_t)NSLOT * slot_floats(D) * sizeof(float);
     off = (off + 127) & ~size_t(127);
-    off += (size_t)NBR * (D + 4) * sizeof(float);
-    off += (size_t)B_PART_FLOATS * sizeof(float);
+    off += batch_xs_bytes(D);
     off += B_SCR_BYTES;
-    off += (size_t)NBR * B_US_PITCH * sizeof(float);
+    off += (size_t)32 * NBR * sizeof(float);
     off += 2 * NBR * sizeof(float) + 8 * NBR * sizeof(float);
     off += (size_t)Vpad * sizeof(float);
     off += 32 * sizeof(uint64_t);
     off += 16 * sizeof(float) + 16 * sizeof(int) + 8 * sizeof(int);
     off += 2 * NBR * sizeof(int);
+    off += 16 * sizeof(unsigned long long);
     off += Vpad;
     return (off + 15) & ~size_t(15);
 }

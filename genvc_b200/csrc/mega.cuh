@@ -48,6 +48,8 @@ struct MegaParams {
     unsigned char* seen_out;    // [B][Vpad]
     int B;         // rows (decode_batch.cu: 1..GV_BATCH_ROWS; decode_mega.cu: 1)
     float* tokx;   // [GV_BATCH_ROWS] sampled tokens of the step, tagged (decode_batch.cu: row r is sampled by CTA r)
+    float* ao;     // [B][D] merged, normalised attention output rows (decode_batch.cu: written by the last item of a (row, head))
+    unsigned* att_cnt;  // [grid * GV_ATTCNT_STRIDE] items finished per (row, head), zero at launch (decode_batch.cu)
     // sampling
     int top_k;
     float top_p, top_p_threshold, temperature, rep_penalty;
@@ -78,6 +80,7 @@ struct MegaParams {
 #define GV_BATCH_NSLOT 10  // ring depth of the batched kernel (its row buffers take the rest of shared memory)
 // exchange tags of one step of the batched kernel: the forward's tags + one for the sampled tokens
 #define GV_BATCH_TAGS_EXTRA 1
+#define GV_ATTCNT_STRIDE 8  // uint32 words between two (row, head) item counters
 
 size_t mega_smem_bytes(int D, int Vpad);
 size_t batch_smem_bytes(int D, int Vpad);

@@ -500,7 +500,8 @@ __device__ __forceinline__ bool ld_tagged_lane(const float* base, int lane, uint
     return ok;
 }
 
-template <int HD, bool DBG>
+// NORM: the item covers all keys of its head (no split): it writes the normalised output, no (max, sum) pair.
+template <int HD, bool DBG, bool NORM = false>
 __device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict__ Vc, const float* xq, int D, int h, int j0, int j1, int S,
                          uint32_t tag_in, float* wml, float* wpart, int tid,
                          float* o_out, float* ml_out, int item, uint32_t tag_out, uint32_t tmask, unsigned long long* dbg) {
@@ -672,8 +673,12 @@ __device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict_
             Lsum = fmaf(wml[2 * w + 1], cw, Lsum);
             os = fmaf(wpart[w * HD + tid], cw, os);
         }
-        st_tagged(o_out, item * HD + tid, os, tag_out);
-        if (tid == 0) st_tagged2(ml_out, item * 2, M, Lsum, tag_out);
+        if constexpr (NORM) {
+            st_tagged(o_out, item * HD + tid, os / Lsum, tag_out);
+        } else {
+            st_tagged(o_out, item * HD + tid, os, tag_out);
+            if (tid == 0) st_tagged2(ml_out, item * 2, M, Lsum, tag_out);
+        }
     }
     if constexpr (DBG) {
       ck[6] = clock64();

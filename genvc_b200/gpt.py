@@ -65,10 +65,12 @@ class GPT:
     # ------------------------------------------------------------------ nn.Module-like surface
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = False):
         """Accepts the checkpoint's flat state dict (keys under ``gpt.``), as
-        ``inference/model_init.py:22`` passes it; tensors outside the path are ignored."""
+        ``inference/model_init.py:22`` passes it; tensors outside the path are ignored.  ``strict=False`` (the
+        reference's call) zero-fills ``gpt.*`` tensors the checkpoint lacks; ``strict=True`` raises on them."""
         self._state_dict = state_dict
+        self._strict = bool(strict)
         if self._engine is not None:
-            self._engine.load_state_dict(state_dict)
+            self._engine.load_state_dict(state_dict, strict=self._strict)
         return self
 
     def load_blob(self, blob: torch.Tensor):
@@ -107,7 +109,7 @@ class GPT:
             if self._blob is not None:
                 self._engine.load_blob(self._blob)
             elif self._state_dict is not None:
-                self._engine.load_state_dict(self._state_dict)
+                self._engine.load_state_dict(self._state_dict, strict=getattr(self, "_strict", False))
         return self
 
     @property

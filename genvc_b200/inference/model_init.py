@@ -36,6 +36,19 @@ class _Unattached:
         self.__getattr__("__call__")
 
 
+def _cfg_get(cfg, path, default):
+    """Nested lookup in an attribute-dict / dict config; ``default`` when any key is absent."""
+    cur = cfg
+    for key in path:
+        if cur is None:
+            return default
+        if isinstance(cur, dict):
+            cur = cur.get(key)
+        else:
+            cur = getattr(cur, key, None)
+    return default if cur is None else cur
+
+
 class GenVCModel:
     """The slice of ``trainers/hifigan_trainer.py::HiFiGANTrainer`` the inference drivers touch."""
 
@@ -44,9 +57,17 @@ class GenVCModel:
         self.dims = GenVCDims.from_config(config)
         self.device = torch.device(device)
         self.gpt = GPT(self.dims, device=device, max_batch=max_batch, max_mel_frames=max_mel_frames)
-        # trainers/hifigan_trainer.py:62-66, 93-95: 24 kHz output / (1024-sample code stride / 4x latent upsampling)
-        self.content_sample_rate = 16000
-        self.hifigan_scale_factor = 4
+        # trainers/hifigan_trainer.py:56: latent upsampling = gpt_code_stride_len / vocoder hop length;
+        # :146: content sample rate = content_dvae_config.audio.dvae_sample_rate.  Read from the checkpoint's config;
+        # the shipped values (1024 / 256 = 4; 16 kHz) only when the keys are absent.
+        self.hifigan_scale_factor = _cfg_get(config, ("vocoder_config", "hop_length"), None)
+        if self.hifigan_scale_factor is not None:
+            self.hifigan_scale_factor = self.dims.code_stride_len / self.hifigan_scale_factor
+            if float(self.hifigan_scale_factor).is_integer():
+                self.hifigan_scale_factor = int(self.hifigan_scale_factor)
+        else:
+            self.hifigan_scale_factor = 4
+        self.content_sample_rate = int(_cfg_get(config, ("content_dvae_config", "audio", "dvae_sample_rate"), 16000))
         self.content_extractor = _Unattached("content_extractor")
         self.content_dvae = _Unattached("content_dvae")
         self.hifigan = _Unattached("hifigan")
