@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <map>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -71,6 +73,15 @@ struct genvc_ctx {
     unsigned long long* trace = nullptr;
     int trace_slots = 0, trace_step = 0;
     int window = 2, dbg_nosync = 0, l2_ahead = 0, hop_settle = 0, hop_hold = 0, hop_near = -1, hop_near_ao = -1;
+
+    // prefill as a CUDA graph: the ~270 launches of the 30 blocks + head are captured once per (batch, prefix length) and
+    // replayed with one launch (the per-op prefill was bound by the host's launch rate: 2.4 ms on one box, 3.5 ms on another)
+    struct PrefillGraph {
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long launches = 0;
+    };
+    std::map<std::pair<int, int>, PrefillGraph> prefill_graphs;
+    bool use_graphs = true;
 
     // host mirror of the generation state
     int B = 0, P = 0;
@@ -207,6 +218,7 @@ int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
     if (g.start_audio < 0 || g.start_audio >= g.n_audio_vocab || g.stop_audio < 0 || g.stop_audio >= g.n_audio_vocab)
         return bad("start/stop audio token outside the vocabulary");
     ctx->layout.build(g);
+    if (const char* e = getenv("GENVC_GRAPH")) ctx->use_graphs = e[0] != '0';
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e == cudaSuccess && device >= 0 && device < ndev) {
@@ -238,7 +250,10 @@ int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
 }
 
 void genvc_destroy(genvc_ctx* ctx) {
-    if (ctx && ctx->blob) gemm_tc_forget(ctx->blob, ctx->blob + ctx->layout.total);
+    if (!ctx) return;
+    if (ctx->blob) gemm_tc_forget(ctx->blob, ctx->blob + ctx->layout.total);
+    for (auto& kv : ctx->prefill_graphs)
+        if (kv.second.exec) (void)cudaGraphExecDestroy(kv.second.exec);
     delete ctx;
 }
 
@@ -334,6 +349,9 @@ int genvc_bind_weights(genvc_ctx* ctx, const float* blob_dev, uint64_t n_floats)
     gemm_tc_forget(blob_dev, blob_dev + ctx->layout.total);
     ctx->blob = blob_dev;
     ctx->stream_packed = false;
+    for (auto& kv : ctx->prefill_graphs)  // captured launches hold the old pointers
+        if (kv.second.exec) (void)cudaGraphExecDestroy(kv.second.exec);
+    ctx->prefill_graphs.clear();
     return GENVC_OK;
 }
 
@@ -383,6 +401,9 @@ int genvc_bind_buffers(genvc_ctx* ctx, float* kv_dev, uint64_t kv_floats, void* 
     ctx->kv = kv_dev;
     ctx->ws = static_cast<char*>(workspace_dev);
     ctx->prefilled = false;
+    for (auto& kv : ctx->prefill_graphs)
+        if (kv.second.exec) (void)cudaGraphExecDestroy(kv.second.exec);
+    ctx->prefill_graphs.clear();
     // exchange tags start at 1 over zeroed buffers
     DevGuard guard(ctx->device);
     CK(guard.err);
@@ -616,10 +637,54 @@ int genvc_prefill(genvc_ctx* ctx, const float* prefix_dev, int B, int P, void* s
     CK(launch_copy_rows(prefix_dev, (long)P * D, X, (long)M * D, B, (long)P * D, st, &ctx->nlaunch));
     CK(launch_embed_mel_rows(nullptr, B, 1, 0, g.start_audio, g.stop_audio, 0, D, ctx->w(L.mel_emb), ctx->w(L.mel_pos),
                              X + (size_t)P * D, (long)M * D, g.n_audio_vocab, ctx->at<int>(ctx->o_flags), st, &ctx->nlaunch));
-    if (int rc = run_blocks(ctx, B, M, 0, nullptr, st)) return rc;
-    if (int rc = run_head(ctx, B, M, P, nullptr, st)) return rc;
-    CK(launch_init_state(ctx->gstate(ctx->gs_cur), ctx->gseen(ctx->gs_cur), B, P, g.n_audio_vocab, ctx->Vpad, g.start_audio, st,
-                         &ctx->nlaunch));
+    // the generation state lives in copy 0 after a prefill (the fused decode launches flip between the two copies)
+    ctx->gs_cur = 0;
+    auto body = [&]() -> int {
+        if (int rc = run_blocks(ctx, B, M, 0, nullptr, st)) return rc;
+        if (int rc = run_head(ctx, B, M, P, nullptr, st)) return rc;
+        CK(launch_init_state(ctx->gstate(0), ctx->gseen(0), B, P, g.n_audio_vocab, ctx->Vpad, g.start_audio, st, &ctx->nlaunch));
+        return GENVC_OK;
+    };
+    bool done = false;
+    // (the tcgen05 GEMM path must be registered before the first capture: launch_gemm_tc sets function attributes once)
+    if (ctx->use_graphs) {
+        const auto key = std::make_pair(B, P);
+        auto it = ctx->prefill_graphs.find(key);
+        if (it == ctx->prefill_graphs.end()) {
+            // first use of this shape: run it eagerly once (sets kernel attributes, warms caches), then capture a second pass
+            if (int rc = body()) return rc;
+            genvc_ctx::PrefillGraph pg;
+            const unsigned long long l0 = ctx->nlaunch;
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                const int rc = body();
+                const cudaError_t e = cudaStreamEndCapture(st, &graph);
+                ok = rc == GENVC_OK && e == cudaSuccess && graph != nullptr;
+            }
+            pg.launches = ctx->nlaunch - l0;
+            ctx->nlaunch = l0;  // nothing ran during the capture
+            if (ok) ok = cudaGraphInstantiate(&pg.exec, graph, 0) == cudaSuccess;
+            if (graph) (void)cudaGraphDestroy(graph);
+            if (!ok) {
+                (void)cudaGetLastError();
+                pg.exec = nullptr;  // remembered as "do not try again": this shape keeps the per-op launches
+            }
+            if (ctx->prefill_graphs.size() >= 64) {  // bounded cache
+                for (auto& kv : ctx->prefill_graphs)
+                    if (kv.second.exec) (void)cudaGraphExecDestroy(kv.second.exec);
+                ctx->prefill_graphs.clear();
+            }
+            ctx->prefill_graphs[key] = pg;
+            done = true;  // the eager pass above did the work
+        } else if (it->second.exec != nullptr) {
+            CK(cudaGraphLaunch(it->second.exec, st));
+            ctx->nlaunch += it->second.launches;
+            done = true;
+        }
+    }
+    if (!done)
+        if (int rc = body()) return rc;
     ctx->B = B;
     ctx->P = P;
     ctx->prefilled = true;

@@ -23,6 +23,23 @@ def shard_units(n_units: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_units, world))
 
 
+def plan_batches(n_units: int, max_rows: int) -> List[List[int]]:
+    """Group ``n_units`` equal-shape units (utterances whose segments have the same lengths) into batches of at most
+    ``max_rows`` rows, as even as possible (the reference batches only equal-length rows: layers/gpt_inference.py:92-96)."""
+    if n_units <= 0:
+        return []
+    if max_rows <= 0:
+        raise ValueError("max_rows must be positive")
+    n_batches = (n_units + max_rows - 1) // max_rows
+    base, extra = divmod(n_units, n_batches)
+    out, start = [], 0
+    for b in range(n_batches):
+        size = base + (1 if b < extra else 0)
+        out.append(list(range(start, start + size)))
+        start += size
+    return out
+
+
 def broadcast_blob(blob: Optional[torch.Tensor], n_floats: int, rank: int, world: int, device) -> torch.Tensor:
     """Rank 0 passes the packed host blob; every rank returns it on ``device``."""
     device = torch.device(device)

@@ -202,3 +202,40 @@ def test_decode_stream_and_cache_sizes_follow_the_layout(L, D, H):
         assert lib.genvc_workspace_bytes(ctx) > 0
     finally:
         lib.genvc_destroy(ctx)
+
+
+def test_plan_batches_and_sharding_cover_the_utterance_set():
+    """BASELINE configs[2]/[3] host logic: a fixed utterance set dealt to the ranks (strong scaling), each rank's share
+    grouped into batches of at most 8 equal-shape rows; every utterance appears exactly once."""
+    from genvc_b200.replicas import plan_batches, shard_units
+
+    for n_utt in (32, 8, 5, 1):
+        for world in (1, 2, 4, 8):
+            seen = []
+            for rank in range(world):
+                mine = shard_units(n_utt, rank, world)
+                groups = plan_batches(len(mine), 8)
+                assert all(1 <= len(gr) <= 8 for gr in groups)
+                assert sorted(i for gr in groups for i in gr) == list(range(len(mine)))
+                if groups:
+                    assert max(len(gr) for gr in groups) - min(len(gr) for gr in groups) <= 1
+                seen += [mine[i] for gr in groups for i in gr]
+            assert sorted(seen) == list(range(n_utt))
+    assert plan_batches(0, 8) == []
+    assert [len(g) for g in plan_batches(32, 8)] == [8, 8, 8, 8]
+    assert [len(g) for g in plan_batches(9, 8)] == [5, 4]
+
+
+def test_bench_config_is_identical_in_both_arms():
+    """The driver compares the ``config`` objects of the two arms of a workload."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for name in ("cfg2", "cfg3", "cfg4"):
+        a, b = bench.config_dict(name), bench.config_dict(name)
+        assert a == b and set(a) == {"workload", "parallelism", "l2"}
+        assert name in a["workload"]
+    assert bench.weight_bytes() == 1515778056
+    assert bench.kv_bytes(60) == 245760 * 60
