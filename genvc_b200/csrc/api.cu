@@ -56,12 +56,13 @@ struct genvc_ctx {
     float* stream = nullptr;
     bool stream_packed = false;
     float* kv = nullptr;
+    float* vw = nullptr;  // projected-value cache of the single-row fused kernel (optional: genvc_bind_vw)
     char* ws = nullptr;
 
     // workspace offsets (bytes)
     size_t o_state, o_seen, state_stride = 0, seen_stride = 0, o_tokx, o_flags, o_status_scratch, o_pend_logits, o_pend_latent, o_splitk, o_X, o_A, o_QKV, o_U;
     // exchange buffers of the fused decode kernel ({value, tag} pairs; one contiguous region)
-    size_t o_xchg, xchg_bytes, o_xq, o_matt_o, o_matt_ml, o_x1, o_pp, o_x2, o_lg, o_hops, o_acc, o_ao, o_attcnt;
+    size_t o_xchg, xchg_bytes, o_xq, o_matt_o, o_matt_ml, o_x1, o_pp, o_x2, o_lg, o_hops, o_acc, o_ao, o_attcnt, o_sbuf;
     size_t hops_bytes = 0;
     size_t acc_bytes = 0;
     uint32_t tag_next = 1;
@@ -86,6 +87,11 @@ struct genvc_ctx {
     // host mirror of the generation state
     int B = 0, P = 0;
     bool prefilled = false, pending = false;
+    bool vw_filled = false;  // the projected-value cache covers the cached positions (false after a prefill until the first fused forward)
+    // The projected-value variant pays once per sequence (its first forward projects the cached V rows: ~0.5 ms at a 48-row
+    // prefix) and saves ~11 us per token: it is used when at least this many tokens may still be generated.
+    int vw_min_tokens = 96;
+    bool seg_pvw = false;    // decided at the first fused launch after a prefill, kept for the sequence
     int n_host = 0;
 
     int D() const { return cfg.d_model; }
@@ -165,6 +171,7 @@ static void plan_workspace(genvc_ctx* c) {
     c->o_lg = w.take(2 * FR * (size_t)c->Vpad * F);
     c->o_tokx = w.take(2 * GV_BATCH_ROWS * F);
     c->o_ao = w.take(2 * FR * D * F);
+    c->o_sbuf = w.take(2 * (size_t)g.n_head * g.max_seq * F);  // scaled attention scores of a step (single-row kernel, PVW)
     // arrival counters (zeroed before every fused launch): the hop counters, then one item counter per (row, head)
     c->o_hops = w.take(HC_COUNT * GV_HOP_STRIDE * sizeof(unsigned));
     c->o_attcnt = w.take((size_t)std::max(c->grid, 1) * GV_ATTCNT_STRIDE * sizeof(unsigned));
@@ -219,6 +226,7 @@ int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
         return bad("start/stop audio token outside the vocabulary");
     ctx->layout.build(g);
     if (const char* e = getenv("GENVC_GRAPH")) ctx->use_graphs = e[0] != '0';
+    if (const char* e = getenv("GENVC_VW_MIN_TOKENS")) ctx->vw_min_tokens = atoi(e);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e == cudaSuccess && device >= 0 && device < ndev) {
@@ -386,6 +394,29 @@ int genvc_pack_stream(genvc_ctx* ctx, float* stream_dev, uint64_t n_floats, void
     ctx->nlaunch += 1;
     ctx->stream = stream_dev;
     ctx->stream_packed = true;
+    return GENVC_OK;
+}
+
+uint64_t genvc_vw_floats(const genvc_ctx* ctx) {
+    if (!ctx || !ctx->mega_ok || ctx->cfg.n_head > 32 || (ctx->cfg.d_model + ctx->grid - 1) / ctx->grid > 8) return 0;
+    return (uint64_t)ctx->cfg.n_layer * ctx->grid * ctx->cfg.max_seq * ctx->cfg.n_head * 8;
+}
+
+int genvc_bind_vw(genvc_ctx* ctx, float* vw_dev, uint64_t n_floats) {
+    if (!ctx) return GENVC_E_INVALID;
+    if (vw_dev == nullptr) {  // unbind: the fused kernel goes back to K / V attention items
+        ctx->vw = nullptr;
+    } else {
+        const uint64_t need = genvc_vw_floats(ctx);
+        if (need == 0) return ctx->fail(GENVC_E_UNSUPPORTED, "no projected-value cache for this shape");
+        if (n_floats < need || reinterpret_cast<uintptr_t>(vw_dev) % 128)
+            return ctx->fail(GENVC_E_INVALID, "projected-value cache too small or misaligned");
+        ctx->vw = vw_dev;
+    }
+    ctx->prefilled = false;
+    for (auto& kv : ctx->prefill_graphs)  // captured prefills bake the pointer (and whether the cache is filled at all)
+        if (kv.second.exec) (void)cudaGraphExecDestroy(kv.second.exec);
+    ctx->prefill_graphs.clear();
     return GENVC_OK;
 }
 
@@ -689,6 +720,7 @@ int genvc_prefill(genvc_ctx* ctx, const float* prefix_dev, int B, int P, void* s
     ctx->P = P;
     ctx->prefilled = true;
     ctx->pending = true;
+    ctx->vw_filled = false;
     ctx->n_host = 0;
     return GENVC_OK;
 }
@@ -741,6 +773,14 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
         p.hops = ctx->at<unsigned>(ctx->o_hops);
         CK(cudaMemsetAsync(p.hops, 0, ctx->hops_bytes, st));
         p.ao = ctx->at<float>(ctx->o_ao); p.att_cnt = ctx->at<unsigned>(ctx->o_attcnt);
+        if (ctx->pending || !ctx->vw_filled)  // first fused launch of the sequence (or after per-op steps): choose the variant
+            ctx->seg_pvw = B == 1 && ctx->vw != nullptr && max_total - ctx->n_host >= ctx->vw_min_tokens;
+        p.vw = ctx->seg_pvw ? ctx->vw : nullptr; p.sbuf = ctx->at<float>(ctx->o_sbuf);
+        // the per-op prefill fills K / V only: the first fused forward after it computes the projected values of the cached
+        // positions from the V cache (the CTA's attn c_proj columns are in shared memory then anyway)
+        const bool runs_forward = n_steps - (ctx->pending ? 1 : 0) >= 1;
+        p.vw_fill = (p.vw != nullptr && !ctx->vw_filled && runs_forward) ? 1 : 0;
+        if (p.vw_fill) ctx->vw_filled = true;
         p.acc = ctx->at<unsigned long long>(ctx->o_acc);
         CK(cudaMemsetAsync(p.acc, 0, ctx->acc_bytes, st));
         {   // exchange tags: unique per (launch, step, layer, buffer); restart over zeroed buffers before a wrap
@@ -778,6 +818,7 @@ int genvc_decode(genvc_ctx* ctx, int n_steps, const genvc_sampling* sp, const fl
     // device-side loop has finished are skipped on the device (GenState::done)
     const Layout& L = ctx->layout;
     const int* skip = &gs->done;
+    ctx->vw_filled = false;  // per-op steps append K / V only: a later fused launch recomputes the projected values
     for (int i = 0; i < n_steps; ++i) {
         const int n = ctx->n_host;
         if (n >= max_total) break;

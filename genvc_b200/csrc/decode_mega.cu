@@ -104,9 +104,138 @@ cudaError_t launch_pack_stream(const StreamDims& s, int layer, int ph, const flo
 }
 
 // ---------------------------------------------------------------------------------------------
+// Projected-value variant (PVW): attn c_proj applied to the VALUE of the position being decoded, per head:
+//   vw[h][u] = sum_{d < hd} v[h hd + d] W_proj[h hd + d][unit u]
+// (the attention output of the step is then sum_j p_{h,j} vw_j[h][u] over the cached projected values: the
+// projection is linear, so it commutes with the softmax-weighted sum, and it no longer waits for the softmax).
+// Unit u of the phase is handled by warp u (<= 8 units); a tile is read by the four warps 4t .. 4t+3, each arrives
+// once.  Lane layout of a head's K range as in the attention item (AttLane): conflict-free vector loads.
+// epi(u, h, value) on lane 8 (h % 4) of warp u; bias(u, c2) once per unit on lane 0.
+// ---------------------------------------------------------------------------------------------
+// L2 load that stays where it is written (the compiler sinks a plain __ldcg to its first use; these are issued early on
+// purpose, microseconds before the values are needed)
+__device__ __forceinline__ float ld_cg_early(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// `fill_n` > 0 (first forward after a prefill): the projected values of the fill_n cached positions are computed here
+// too, while this CTA's attn c_proj columns are in shared memory anyway -- warp w takes positions w, w + 8, ..., all
+// units, values straight from the V cache (vfill: [H][S_max][hd]), results to out_fill[(pos H + h) 8 + unit].
+template <int NXV, int HD, class Epi, class Bias>
+__device__ __forceinline__ void gemv_heads(const Ring& ring, const Cons& cs, int nunits, const float* xs, int warp, int lane, Epi epi,
+                                           Bias bias, int fill_n, const float* vfill, int S_max, float* out_fill) {
+    constexpr int D = NXV * 128, UF = D + 4, H = D / HD;
+    using L = AttLane<HD>;
+    constexpr int VEC = L::VEC, NCH = L::NCH, DPL = L::DPL;
+    const int ntiles = (nunits + UPT - 1) / UPT;
+    if (fill_n > 0) {  // uniform over the CTA
+        if (lane < ntiles) tile_ready_wait(ring, cs.gt + (uint32_t)lane);
+        __syncwarp();
+        // (Once per generated sequence; the host enables this variant only for generations long enough to amortise it.
+        // A software-pipelined version with two positions in flight per warp needed 64 more live registers and slowed
+        // the whole kernel down.)
+        for (int pos = warp; pos < fill_n; pos += MEGA_WARPS) {
+            float vr[H][DPL];
+#pragma unroll
+            for (int h = 0; h < H; ++h)
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+                    ld_vec<VEC>(vfill + ((size_t)h * S_max + pos) * HD + (c * 32 + lane) * VEC, vr[h] + c * VEC);
+            for (int u = 0; u < nunits; ++u) {
+                const float* col = slot_ptr(ring, cs.gt + (uint32_t)(u >> 2)) + (u & 3) * UF;
+#pragma unroll
+                for (int hg = 0; hg < H; hg += 4) {
+                    float tot[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float a = 0.0f;
+                        if (hg + q < H) {
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c) {
+                                const int off = (hg + q) * HD + (c * 32 + lane) * VEC;
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) a = fmaf(col[off + e], vr[(hg + q) < H ? (hg + q) : 0][c * VEC + e], a);
+                            }
+                        }
+                        tot[q] = a;
+                    }
+                    const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+                    const float k0 = up16 ? tot[2] : tot[0], s0 = up16 ? tot[0] : tot[2];
+                    const float k1 = up16 ? tot[3] : tot[1], s1 = up16 ? tot[1] : tot[3];
+                    const float h0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+                    const float h1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+                    const float keep = up8 ? h1 : h0, send = up8 ? h0 : h1;
+                    float v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    const int q = lane >> 3;
+                    if ((lane & 7) == 0 && hg + q < H) __stcg(out_fill + ((size_t)pos * H + hg + q) * 8 + u, v);
+                }
+            }
+        }
+        bar_sync(1, MEGA_CONSUMERS);  // every warp read both tiles: nobody releases one before all are done
+    }
+    const int t = warp >> 2;
+    if (t >= ntiles) return;
+    if (lane == 0) tile_ready_wait(ring, cs.gt + (uint32_t)t);
+    __syncwarp();
+    if (warp < nunits) {
+        const float* col = slot_ptr(ring, cs.gt + (uint32_t)t) + (warp & 3) * UF;
+        if (lane == 0) bias(warp, col[D]);
+#pragma unroll
+        for (int hg = 0; hg < H; hg += 4) {
+            float tot[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float a = 0.0f;
+                if (hg + q < H) {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const int off = (hg + q) * HD + (c * 32 + lane) * VEC;
+                        if constexpr (VEC == 4) {
+                            const float4 wv = *reinterpret_cast<const float4*>(col + off);
+                            const float4 xv = *reinterpret_cast<const float4*>(xs + off);
+                            a = fmaf(wv.x, xv.x, a);
+                            a = fmaf(wv.y, xv.y, a);
+                            a = fmaf(wv.z, xv.z, a);
+                            a = fmaf(wv.w, xv.w, a);
+                        } else if constexpr (VEC == 2) {
+                            const float2 wv = *reinterpret_cast<const float2*>(col + off);
+                            const float2 xv = *reinterpret_cast<const float2*>(xs + off);
+                            a = fmaf(wv.x, xv.x, a);
+                            a = fmaf(wv.y, xv.y, a);
+                        } else {
+                            a = fmaf(col[off], xs[off], a);
+                        }
+                    }
+                }
+                tot[q] = a;
+            }
+            // transposing butterfly: lanes [8q, 8q+8) end up reducing tot[q]
+            const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+            const float k0 = up16 ? tot[2] : tot[0], s0 = up16 ? tot[0] : tot[2];
+            const float k1 = up16 ? tot[3] : tot[1], s1 = up16 ? tot[1] : tot[3];
+            const float h0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+            const float h1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+            const float keep = up8 ? h1 : h0, send = up8 ? h0 : h1;
+            float v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            const int q = lane >> 3;
+            if ((lane & 7) == 0 && hg + q < H) epi(warp, hg + q, v);
+        }
+    }
+    tile_release(ring, cs.gt + (uint32_t)t, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int NXV, bool TRACE>
+template <int NXV, bool TRACE, bool PVW>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int D = NXV * 128;
@@ -150,6 +279,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     off += 16 * sizeof(float);
     int* iscr = reinterpret_cast<int*>(smem_raw + off);
     off += 16 * sizeof(int);
+    float* vwn = reinterpret_cast<float*>(smem_raw + off);  // PVW: [H][8] projected value of the position being decoded
+    float* pbias = vwn + 32 * 8;                             // PVW: [8] attn c_proj bias of this CTA's columns
+    off += (32 * 8 + 8) * sizeof(float);
     volatile int* ctl = reinterpret_cast<volatile int*>(smem_raw + off);  // [0] stop flag, [1] tiles consumed, [2] token
     ring.landed = reinterpret_cast<uint32_t*>(smem_raw + off) + 3;        // [3] tiles the producer has seen landed
     volatile int* hold = reinterpret_cast<volatile int*>(smem_raw + off) + 4;  // [4] consumers are inside a hop: producer pauses
@@ -332,6 +464,178 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     cs.gt += (uint32_t)ntl[PH_QKV];
                     stamp(ts + 2);
                 }
+                if constexpr (PVW) {
+                // ---- projected-value variant: scores-only items, attn c_proj applied to the new VALUE (off the softmax's
+                // critical path), softmax + weighted sum of the cached projected values in every CTA for its own columns ----
+                hop_arrive(hc + HC_XQ * GV_HOP_STRIDE, tid);  // q | k | v of this layer are on their way (hint; tags validate)
+                if (cta < n_items) {
+                    const int h = cta / nsplit, sp = cta % nsplit;
+                    const int j0 = sp * chunk, j1 = min(S, j0 + chunk);
+                    float* kh = kc + (size_t)h * p.S_max * HD;
+                    float* vh = vc + (size_t)h * p.S_max * HD;
+#define GV_ATT_CASE(hd)                                                                                                       \
+    case hd:                                                                                                                  \
+        score_item<hd>(kh, vh, p.xq, D, h, j0, j1, S, tg + TG_XQ, att_sc + 16, tid, p.sbuf + 2 * (size_t)h * p.S_max, tg + TG_AO, \
+                       tmask);                                                                                                \
+        break;
+                    switch (HD) {
+                        GV_ATT_CASE(32) GV_ATT_CASE(64) GV_ATT_CASE(128) GV_ATT_CASE(256)
+                        default: break;
+                    }
+#undef GV_ATT_CASE
+                    hop_arrive(hc + HC_AO * GV_HOP_STRIDE, tid);
+                }
+                t_ao += (unsigned)n_items;
+                stamp(ts + 3);
+                {
+                    float* vw_slice = p.vw + ((size_t)l * G + cta) * (size_t)p.S_max * H * 8;  // [pos][h][8]
+                    float* psm = part;                         // [heads of the pass][S] probabilities (scratch region)
+                    const int psm_cap = 9728 / 4 - 64;
+                    float* redsm = part + psm_cap;             // [8 warps][8 columns]
+                    const int HG = max(1, min(H, psm_cap / S));
+                    const int colj = tid & 7, g = tid >> 3;
+                    // request this thread's first eight cached projected values now: their addresses depend only on the
+                    // position, and the rows come from HBM (the weight stream sweeps L2 once per token)
+                    // first forward after a prefill: the cached positions have no projected values yet (computed below)
+                    const int fill_n = (p.vw_fill && fwd == 1u) ? S - 1 : 0;
+                    const bool prefetched = HG == H && fill_n == 0;
+                    float vwv[8];
+                    if (prefetched) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int qq = g + 32 * k;
+                            vwv[k] = (qq < (S - 1) * H) ? ld_cg_early(vw_slice + (size_t)qq * 8 + colj) : 0.0f;
+                        }
+                    }
+                    // v of the position being decoded -> xo (the input of the per-head attn c_proj GEMV)
+                    hop_wait(hc + HC_XQ * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near);
+                    stamp(ts + 14);
+                    if (xvalid) {
+                        float4 v4;
+                        ld_tagged_vec<4>(p.xq, 2 * D + 4 * tid, tg + TG_XQ, tmask, &v4.x);
+                        *reinterpret_cast<float4*>(xo + 4 * tid) = v4;
+                    }
+                    if (hold_c && tid == 0) *hold_c = 0;
+                    bar_sync(1, MEGA_CONSUMERS);
+                    stamp(ts + 15);
+                    const int np = nun[PH_PROJ];
+                    float* vw_new = vw_slice + (size_t)(S - 1) * H * 8;
+                    // The scores are usually complete by now (the items need q only): see them arrive, request this warp's
+                    // first 128 scores, and let the loads fly while the per-head GEMV runs.
+                    // (no counter wait: a score that is not there yet is spun on below -- the items only need q, so the
+                    // scores land well before the value hop above has completed)
+                    stamp(ts + 16);
+                    uint2 sa[4];
+                    if (warp < min(HG, H)) {
+                        const float* sb = p.sbuf + 2 * (size_t)warp * p.S_max;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (lane + 32 * k < S) sa[k] = ld_x8(sb + 2 * (size_t)(lane + 32 * k));
+                    }
+                    auto epi = [&](int u, int h, float v) {
+                        vwn[h * 8 + u] = v;
+                        __stcg(vw_new + h * 8 + u, v);
+                    };
+                    auto bia = [&](int u, float c2) { pbias[u] = c2; };
+#define GV_HEADS_CASE(hd)                                                                    \
+    case hd:                                                                                 \
+        if constexpr (D % hd == 0 && D / hd <= 32)                                           \
+            gemv_heads<NXV, hd>(ring, cs, np, xo, warp, lane, epi, bia, fill_n, vc, p.S_max, vw_slice); \
+        break;
+                    switch (HD) {
+                        GV_HEADS_CASE(32) GV_HEADS_CASE(64) GV_HEADS_CASE(128) GV_HEADS_CASE(256)
+                        default: break;
+                    }
+#undef GV_HEADS_CASE
+                    cs.gt += (uint32_t)ntl[PH_PROJ];
+                    stamp(ts + 4);
+                    // scores of all heads -> softmax -> weighted sum of the projected values (this CTA's columns)
+                    float acc = 0.0f;
+                    const int hshift = (H & (H - 1)) == 0 ? __ffs(H) - 1 : -1;  // pairs -> (position, head) without a division
+                    for (int h0 = 0; h0 < H; h0 += HG) {
+                        const int nh = min(HG, H - h0);
+                        // one head per warp: scores straight from L2 (four tagged loads in flight per lane), fp32 softmax as
+                        // HF computes it, probabilities -> shared memory
+                        for (int hh = warp; hh < nh; hh += MEGA_WARPS) {
+                            float* ph = psm + hh * S;
+                            const float* sb = p.sbuf + 2 * (size_t)(h0 + hh) * p.S_max;
+                            const uint32_t tgs = tg + TG_AO;
+                            float m = -INFINITY;
+                            for (int j4 = lane; j4 < S; j4 += 128) {
+                                uint2 a[4];
+                                const bool pre = h0 == 0 && hh == warp && j4 == lane;  // requested before the GEMV
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (j4 + 32 * k < S) a[k] = pre ? sa[k] : ld_x8(sb + 2 * (size_t)(j4 + 32 * k));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (j4 + 32 * k < S) {
+                                        uint32_t spins = 0;
+                                        while (((a[k].y ^ tgs) & tmask) != 0u) {
+                                            if (++spins > MEGA_SPIN_LIMIT) __trap();
+                                            a[k] = ld_x8(sb + 2 * (size_t)(j4 + 32 * k));
+                                        }
+                                        const float sv = __uint_as_float(a[k].x);
+                                        ph[j4 + 32 * k] = sv;
+                                        m = fmaxf(m, sv);
+                                    }
+                                }
+                            }
+                            m = warp_max(m);
+                            float sum = 0.0f;
+                            for (int jj = lane; jj < S; jj += 32) {
+                                const float e = expf(ph[jj] - m);
+                                ph[jj] = e;
+                                sum += e;
+                            }
+                            sum = warp_sum(sum);
+                            const float inv = 1.0f / sum;
+                            for (int jj = lane; jj < S; jj += 32) ph[jj] *= inv;
+                        }
+                        if (hold_c && tid == 0) *hold_c = 0;
+                        bar_sync(1, MEGA_CONSUMERS);
+                        stamp(ts + 18);
+                        // cached positions: (j, head) pairs dealt to the 32 thread groups; 8 consecutive threads read one
+                        // 32-byte row segment of the slice.  The first eight pairs of every thread were requested from
+                        // the cache at the start of the section (single pass only).
+                        const int npairs = (S - 1) * nh;
+                        int q = g;
+                        if (prefetched) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int qq = g + 32 * k;
+                                if (qq < npairs) {  // (single pass: nh == H)
+                                    const int jj = hshift >= 0 ? (qq >> hshift) : qq / nh, hh = qq - jj * nh;
+                                    acc = fmaf(psm[hh * S + jj], vwv[k], acc);
+                                }
+                            }
+                            q = g + 256;
+                        }
+                        for (; q < npairs; q += 32) {
+                            const int jj = q / nh, hh = q - jj * nh;
+                            acc = fmaf(psm[hh * S + jj], ldcg(vw_slice + ((size_t)jj * H + h0 + hh) * 8 + colj), acc);
+                        }
+                        if (g == 0)  // the position being decoded: its projected value is still in shared memory
+                            for (int hh = 0; hh < nh; ++hh) acc = fmaf(psm[hh * S + S - 1], vwn[(h0 + hh) * 8 + colj], acc);
+                        bar_sync(1, MEGA_CONSUMERS);  // psm is rewritten by the next pass / redsm follows
+                        stamp(ts + 19);
+                    }
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                    if (lane < 8) redsm[warp * 8 + lane] = acc;
+                    bar_sync(1, MEGA_CONSUMERS);
+                    if (tid < np) {
+                        float o = 0.0f;
+#pragma unroll
+                        for (int w = 0; w < MEGA_WARPS; ++w) o += redsm[w * 8 + tid];
+                        const int col = ubeg[PH_PROJ] + tid;
+                        st_tagged(p.x1, col, xres0[col] + (o + pbias[tid]), tg + TG_X1);
+                    }
+                    stamp(ts + 5);
+                    stamp_wait(ts + 12);
+                    hop_arrive(hc + HC_X1 * GV_HOP_STRIDE, tid);
+                }
+                } else {
                 // ---- ATT: (head, key-range) items on the first n_items CTAs ----
                 if (cta < n_items) {
                     const int h = cta / nsplit, sp = cta % nsplit;
@@ -407,6 +711,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     stamp(ts + 5);
                     stamp_wait(ts + 12);
                     hop_arrive(hc + HC_X1 * GV_HOP_STRIDE, tid);
+                }
                 }
                 // ---- FC + P2: u = gelu_new(LN2(x1) . W_fc + b) (kept in this CTA) -> partial of u . W_proj2 ----
                 {
@@ -641,22 +946,25 @@ size_t mega_smem_bytes(int D, int Vpad) {
     off += (size_t)Vpad * sizeof(float) + 3 * (size_t)D * sizeof(float);
     off += 32 * sizeof(uint64_t);
     off += (32 + 64 + 16) * sizeof(float) + 16 * sizeof(int) + 8 * sizeof(int);
+    off += (32 * 8 + 8) * sizeof(float);
     off += Vpad;
     return (off + 15) & ~size_t(15);
 }
 
-template <int NXV, bool TRACE>
+template <int NXV, bool TRACE, bool PVW>
 static cudaError_t launch_nxv2(const MegaParams& p, int grid, size_t smem, cudaStream_t st) {
     cudaError_t e =
-        cudaFuncSetAttribute(decode_mega_kernel<NXV, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(decode_mega_kernel<NXV, TRACE, PVW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     MegaParams pp = p;
     void* args[] = {&pp};
-    return cudaLaunchCooperativeKernel((void*)decode_mega_kernel<NXV, TRACE>, dim3(grid), dim3(MEGA_THREADS), args, smem, st);
+    return cudaLaunchCooperativeKernel((void*)decode_mega_kernel<NXV, TRACE, PVW>, dim3(grid), dim3(MEGA_THREADS), args, smem, st);
 }
 template <int NXV>
 static cudaError_t launch_nxv(const MegaParams& p, int grid, size_t smem, cudaStream_t st) {
-    return p.trace != nullptr ? launch_nxv2<NXV, true>(p, grid, smem, st) : launch_nxv2<NXV, false>(p, grid, smem, st);
+    if (p.vw != nullptr)
+        return p.trace != nullptr ? launch_nxv2<NXV, true, true>(p, grid, smem, st) : launch_nxv2<NXV, false, true>(p, grid, smem, st);
+    return p.trace != nullptr ? launch_nxv2<NXV, true, false>(p, grid, smem, st) : launch_nxv2<NXV, false, false>(p, grid, smem, st);
 }
 
 cudaError_t launch_decode_mega(const MegaParams& p, int grid, cudaStream_t st) {

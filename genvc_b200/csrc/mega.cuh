@@ -14,7 +14,7 @@ enum { HC_XQ = 0, HC_AO = 1, HC_X1 = 2, HC_PP = 3, HC_X2 = 4, HC_LG = 5, HC_COUN
 // exchange tags of one forward: tag(layer l, buffer b) = tbase + GV_TAGS_PER_LAYER*l + b; logits = tbase + GV_TAGS_PER_LAYER*L
 #define GV_TAGS_PER_LAYER 5
 // debug timeline slots per layer (genvc_debug_trace)
-#define GV_TRACE_PER_LAYER 20
+#define GV_TRACE_PER_LAYER 28
 
 struct MegaParams {
     int L, D, H, V, Vpad, S_max;
@@ -50,6 +50,10 @@ struct MegaParams {
     float* tokx;   // [GV_BATCH_ROWS] sampled tokens of the step, tagged (decode_batch.cu: row r is sampled by CTA r)
     float* ao;     // [B][D] merged, normalised attention output rows (decode_batch.cu: written by the last item of a (row, head))
     unsigned* att_cnt;  // [grid * GV_ATTCNT_STRIDE] items finished per (row, head), zero at launch (decode_batch.cu)
+    // projected-value variant of the single-row kernel (decode_mega.cu, PVW): null = classic K / V attention items
+    float* vw;     // [L][grid][S_max][H][8] cache of v_j . W_proj per head, sliced by the CTA that owns the output columns
+    float* sbuf;   // [H][S_max] scaled attention scores of the step, tagged
+    int vw_fill;   // 1: the first forward of this launch computes the projected values of all cached positions (after a prefill)
     // sampling
     int top_k;
     float top_p, top_p_threshold, temperature, rep_penalty;

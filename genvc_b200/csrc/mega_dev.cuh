@@ -695,6 +695,118 @@ __device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Scores-only attention item (projected-value cache variant of the single-row kernel, decode_mega.cu): the item
+// computes s_j = (q . k_j) / sqrt(hd) for its key range and publishes the raw scaled scores; softmax and the weighted
+// sum run in every CTA against the cache of PROJECTED values (v_j . W_proj, per head), so there is no P.V product, no
+// partial-output merge and no barrier after q here: prefetch K rows, poll q, dots, one shuffle tree, tagged stores.
+// The warp that owns the position being decoded also takes k / v of this step from the exchange buffer, appends them
+// to the K / V caches (the V cache stays complete for the per-op path) and scores the new key.
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+__device__ __noinline__ void score_item(float* __restrict__ Kc, float* __restrict__ Vc, const float* xq, int D, int h, int j0, int j1,
+                                        int S, uint32_t tag_in, float* qs, int tid, float* s_out, uint32_t tag_out, uint32_t tmask) {
+    using L = AttLane<HD>;
+    constexpr int VEC = L::VEC, NCH = L::NCH, DPL = L::DPL;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nk = j1 - j0;
+    const int nb = (nk + 31) >> 5;
+    const int jn = S - 1 - j0;  // relative index of the position being decoded (inside this item iff 0 <= jn < nk)
+    const bool mine = jn >= 0 && jn < nk && ((jn & 31) >> 2) == warp;  // this warp owns the new position
+    const int bn = jn >> 5;
+    const float sqrt_hd = sqrtf((float)HD);
+    auto load_row = [&](const float* base, int jr, float* dst) {  // cache row of relative key jr (zeros outside / new key)
+        if (jr < nk && jr != jn) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) ld_vec<VEC>(base + (size_t)(j0 + jr) * HD + (c * 32 + lane) * VEC, dst + c * VEC);
+        } else {
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) dst[i] = 0.0f;
+        }
+    };
+    float kr[ATT_ROWS][DPL];
+#pragma unroll
+    for (int u = 0; u < ATT_ROWS; ++u) load_row(Kc, warp * ATT_ROWS + u, kr[u]);
+    float qr[DPL], knew[DPL], vnew[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) knew[i] = vnew[i] = 0.0f;
+    {
+        const float* qp = xq + 2 * (size_t)(h * HD);
+        const float* kp = xq + 2 * (size_t)(D + h * HD);
+        const float* vp = xq + 2 * (size_t)(2 * D + h * HD);
+        constexpr int EPW = HD / MEGA_WARPS;
+        float qmine = 0.0f;
+        uint32_t spins = 0;
+        bool ok = false;
+        while (!ok) {
+            ok = true;
+            if (lane < EPW) {
+                const uint2 a = ld_x8(qp + 2 * (warp * EPW + lane));
+                ok = ((a.y ^ tag_in) & tmask) == 0u;
+                qmine = __uint_as_float(a.x);
+            }
+            if (mine) {
+                const bool ok_k = ld_tagged_lane<VEC, NCH>(kp, lane, tag_in, tmask, knew);
+                const bool ok_v = ld_tagged_lane<VEC, NCH>(vp, lane, tag_in, tmask, vnew);
+                ok = ok && ok_k && ok_v;
+            }
+            ok = __all_sync(0xffffffffu, ok);
+            if (++spins > MEGA_SPIN_LIMIT) __trap();
+        }
+        if (lane < EPW) qs[warp * EPW + lane] = qmine;
+        bar_sync(1, MEGA_CONSUMERS);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) qr[c * VEC + i] = qs[(c * 32 + lane) * VEC + i];
+    }
+    if (mine) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            st_vec<VEC>(Kc + (size_t)(S - 1) * HD + (c * 32 + lane) * VEC, knew + c * VEC);
+            st_vec<VEC>(Vc + (size_t)(S - 1) * HD + (c * 32 + lane) * VEC, vnew + c * VEC);
+        }
+    }
+    for (int b = 0; b < nb; ++b) {
+        const int r0 = b * 32 + warp * ATT_ROWS;
+        const bool with_new = mine && b == bn;  // warp-uniform
+        float sc[ATT_ROWS + 1];
+#pragma unroll
+        for (int u = 0; u < ATT_ROWS; ++u) {
+            float a = 0.0f;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) a = fmaf(qr[i], kr[u][i], a);
+            sc[u] = a;
+        }
+        {
+            float a = 0.0f;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) a = fmaf(qr[i], knew[i], a);
+            sc[ATT_ROWS] = a;
+        }
+        if (b + 1 < nb) {
+#pragma unroll
+            for (int u = 0; u < ATT_ROWS; ++u) load_row(Kc, r0 + 32 + u, kr[u]);
+        }
+#pragma unroll
+        for (int x = 16; x > 0; x >>= 1) {
+#pragma unroll
+            for (int u = 0; u <= ATT_ROWS; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], x);
+        }
+        // lane u publishes row u of the batch (lane ATT_ROWS: the new position)
+        float mys = sc[0];
+#pragma unroll
+        for (int u = 1; u <= ATT_ROWS; ++u) mys = (lane == u) ? sc[u] : mys;
+        // s / sqrt(hd): for hd = 64, 256 the divisor is a power of two and the product with its reciprocal is the same
+        mys = (HD == 64 || HD == 256) ? mys * (1.0f / sqrt_hd) : mys / sqrt_hd;
+        if (lane < ATT_ROWS) {
+            if (r0 + lane < nk && r0 + lane != jn) st_tagged(s_out, j0 + r0 + lane, mys, tag_out);
+        } else if (lane == ATT_ROWS && with_new) {
+            st_tagged(s_out, S - 1, mys, tag_out);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // producer: one thread walks the CTA's weight stream through the ring
 // ---------------------------------------------------------------------------------------------
 struct Producer {

@@ -95,6 +95,13 @@ class Engine:
             self.ws = torch.zeros(int(self.lib.genvc_workspace_bytes(self._ctx)), dtype=torch.uint8, device=self.device)
         self._check(self.lib.genvc_bind_buffers(self._ctx, self.kv.data_ptr(), self.kv.numel(), self.ws.data_ptr(),
                                                 self.ws.numel()))
+        # projected-value cache of the single-row fused kernel (0.6 GB at L=30, H=4; GENVC_VW=0 keeps the K / V items)
+        self.vw: Optional[torch.Tensor] = None
+        n_vw = int(self.lib.genvc_vw_floats(self._ctx))
+        if n_vw > 0 and os.environ.get("GENVC_VW", "1") != "0":
+            with torch.cuda.device(self.device):
+                self.vw = torch.zeros(n_vw, dtype=torch.float32, device=self.device)
+            self._check(self.lib.genvc_bind_vw(self._ctx, self.vw.data_ptr(), n_vw))
         self._B = 0
         self._P = 0
         self._pending = False  # logits of the next step already computed (by prefill)
@@ -282,7 +289,7 @@ class Engine:
             self._check(self.lib.genvc_debug_trace(self._ctx, None, 0, 0))
             self._trace = None
             return None
-        slots = self.dims.n_layer * 20 + 8
+        slots = self.dims.n_layer * 28 + 8
         g = self.decode_grid
         self._trace = torch.zeros(g * slots, dtype=torch.int64, device=self.device)
         self._check(self.lib.genvc_debug_trace(self._ctx, self._trace.data_ptr(), slots, int(step)))

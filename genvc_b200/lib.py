@@ -62,6 +62,8 @@ SIGNATURES = {
     "genvc_kv_floats": (C.c_uint64, [_P]),
     "genvc_workspace_bytes": (C.c_uint64, [_P]),
     "genvc_bind_buffers": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64]),
+    "genvc_vw_floats": (C.c_uint64, [_P]),
+    "genvc_bind_vw": (C.c_int, [_P, _P, C.c_uint64]),
     "genvc_perceiver": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "genvc_embed_prefix": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "genvc_prefill": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),

@@ -122,6 +122,15 @@ uint64_t genvc_workspace_bytes(const genvc_ctx* ctx);
 int genvc_bind_buffers(genvc_ctx* ctx, float* kv_dev, uint64_t kv_floats,
                        void* workspace_dev, uint64_t workspace_bytes);
 
+/* Optional projected-value cache of the single-row fused decode kernel: [L][grid][max_seq][H][8] floats holding
+ * v_j . W_proj per head and position, sliced by the CTA that owns the output columns.  attn c_proj is linear, so the
+ * kernel applies it to the new value while the softmax is still being computed and sums cached projected values
+ * instead of merging partial attention outputs (HF GPT2Attention: attn_output = c_proj(softmax(q k^T) v); same
+ * arithmetic, different association).  genvc_prefill fills the prefix rows (batch 1).  NULL unbinds it.
+ * genvc_vw_floats returns 0 when the shape has no such variant. */
+uint64_t genvc_vw_floats(const genvc_ctx* ctx);
+int genvc_bind_vw(genvc_ctx* ctx, float* vw_dev, uint64_t n_floats);
+
 /* ---- the path -------------------------------------------------------------- */
 
 /* GPT.get_style_emb -> PerceiverResampler.forward (layers/gpt.py:351-373,

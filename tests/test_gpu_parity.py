@@ -160,6 +160,48 @@ def test_fused_long_context_matches_per_op(name, T, n, cuda_device):
     assert ok, f"latent max err {err}"
 
 
+@pytest.mark.parametrize("name", TOY + ["full_h4_topk20", "full_h16_greedy"])
+def test_projected_value_variant_matches_fixtures(name, cuda_device, monkeypatch):
+    """The single-row fused kernel has two attention arrangements: K / V items, and (for generations of >= 96 tokens) a
+    cache of PROJECTED values v_j . W_proj with scores-only items (attn c_proj is linear, so it commutes with the
+    softmax-weighted sum).  Forced on for every fixture here: ids bit-exact, latents / teacher-forced logits in tolerance,
+    including the lazy projection of the prefix rows at the first forward and a switch per-op -> fused mid-sequence."""
+    from genvc_b200.config import GenVCDims
+    from genvc_b200.engine import Sampling
+    from genvc_b200.gpt import GPT
+
+    monkeypatch.setenv("GENVC_VW_MIN_TOKENS", "1")
+    fx = load_golden(name)
+    ck = golden_checkpoint(fx)
+    g = GPT(GenVCDims.from_config(ck["config"]), device=cuda_device)
+    g.load_state_dict(ck["model"])
+    g.eval().to(cuda_device).init_gpt_for_inference()
+    assert g.engine.vw is not None
+    ids, lats = _run_generate(fx, g, cuda_device, 2)
+    assert torch.equal(ids.cpu(), fx["ids"]), f"first mismatch at {(ids.cpu() != fx['ids']).nonzero()[:1].tolist()}"
+    ok, err = close(lats[:, fx["steps"].to(lats.device)], fx["latents"], LAT_ATOL, LAT_RTOL)
+    assert ok, f"latent max err {err}"
+    # teacher-forced: the first 5 steps through the per-op kernels (K / V caches only), the rest fused (the projected values
+    # of everything cached so far are computed at its first forward)
+    n = min(fx["ids"].shape[1], 48)
+    eng = g.engine
+    cond = fx["style_emb"].transpose(1, 2).contiguous().to(cuda_device)
+    g.compute_embeddings(cond, fx["codes"].to(cuda_device))
+    eng.prefill(g._prefix)
+    sp = Sampling(**fx["sampling"], max_new_tokens=n)
+    forced = fx["ids"][:, :n].transpose(0, 1).contiguous().to(cuda_device)
+    k = min(5, n - 1)
+    ch1 = eng.decode(k, sp, forced=forced[:k], want_logits=True, mode=1)
+    ch2 = eng.decode(n - k, sp, forced=forced[k:], want_logits=True, mode=2)
+    assert ch1.status.tolist()[0] == k and ch2.status.tolist()[0] == n - k
+    logits = torch.cat([ch1.logits, ch2.logits], 0).transpose(0, 1)
+    steps = fx["steps"][fx["steps"] < n]
+    ok, err = close(logits[:, steps.to(cuda_device)], fx["logits"][:, : len(steps)], LOGIT_ATOL, LOGIT_RTOL)
+    assert ok, f"logit max err {err}"
+    del g
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("name", FULL)
 def test_full_size_token_ids_bit_exact(name, cuda_device):
     """BASELINE configs[0] and friends at L=30, D=1024: free-running ids through the fused kernel."""

@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 # trace slots per layer (include/genvc_b200.h)
-TPL = 20
+TPL = 28
 SEGMENTS = [
     ("x2 hop + load", None, 0), ("LN1", 0, 1), ("QKV gemv", 1, 2), ("attention item", 2, 3), ("AO hop + merge", 3, 4),
     ("PROJ gemv", 4, 5), ("x1 hop + load", 5, 6), ("LN2", 6, 7), ("FC gemv", 7, 8), ("P2 gemv", 8, 9), ("PP hop", 9, 10),
@@ -64,6 +64,13 @@ def analyse(tr: torch.Tensor, L: int) -> dict:
         "logits hop + load": float((tr[:, head + 2] - tr[:, head + 1]).median()),
         "sample": float((tr[:, head + 3] - tr[:, head + 2]).median()),
     }
+    # projected-value variant: stamps 14..19 are absolute times inside the PROJ section
+    pv = tr[:, : L * TPL].view(G, L, TPL)[:, 1:, :]
+    if float(pv[:, :, 14].max()) > 1e15:  # (globaltimer values, not cycle counts)
+        names = ["score item->xq hop seen", "v load", "score hop wait", "per-head proj gemv", "scores validated+max", "exp+sum+scale", "barrier",
+                 "8 fma", "new position", "barrier2", "reduce+store"]
+        idx = [(3, 14), (14, 15), (15, 16), (16, 4), (4, 20), (20, 21), (21, 18), (18, 22), (22, 23), (23, 19), (19, 5)]
+        out["pvw_ns"] = {n: float((pv[:, :, b] - pv[:, :, a]).median()) for n, (a, b) in zip(names, idx)}
     att = ww[:, 1:, 14:20]
     sel = att[:, :, 0] > 0
     out["att_cycles"] = [float(att[:, :, k][sel].median()) if sel.any() else 0.0 for k in range(6)]
@@ -123,6 +130,8 @@ def main():
         for name, a in v["segments"].items():
             print(f"  {name:20s} med {a['med']/1e3:6.2f} us  max {a['max']/1e3:6.2f}  critical-path {a['crit']/1e3:6.2f}")
         print("  head:", {n: round(x / 1e3, 2) for n, x in v["head"].items()})
+        if "pvw_ns" in v:
+            print("  projected-value section (median over CTAs and layers, us):", {n: round(x / 1e3, 2) for n, x in v["pvw_ns"].items()})
         print("  attention item cycles (prefetch issue, poll until q seen, dots+shuffles, softmax weights+PV, later batches, barrier+merge+store):", [int(x) for x in v["att_cycles"]])
         print("  weight wait per layer (thread 0):", {n: int(x) for n, x in v["weight_wait_ns"].items()}, "cycles")
 
