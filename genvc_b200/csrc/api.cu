@@ -62,7 +62,7 @@ struct genvc_ctx {
     // workspace offsets (bytes)
     size_t o_state, o_seen, state_stride = 0, seen_stride = 0, o_tokx, o_flags, o_status_scratch, o_pend_logits, o_pend_latent, o_splitk, o_X, o_A, o_QKV, o_U;
     // exchange buffers of the fused decode kernel ({value, tag} pairs; one contiguous region)
-    size_t o_xchg, xchg_bytes, o_xq, o_matt_o, o_matt_ml, o_x1, o_pp, o_x2, o_lg, o_hops, o_acc, o_ao, o_attcnt, o_sbuf;
+    size_t o_xchg, xchg_bytes, o_xq, o_matt_o, o_matt_ml, o_x1, o_pp, o_x2, o_lg, o_hops, o_acc, o_ao, o_attcnt, o_sbuf, o_tcptr, o_gbar;
     size_t hops_bytes = 0;
     size_t acc_bytes = 0;
     uint32_t tag_next = 1;
@@ -83,6 +83,14 @@ struct genvc_ctx {
     };
     std::map<std::pair<int, int>, PrefillGraph> prefill_graphs;
     bool use_graphs = true;
+    // persistent fused prefill (gemm_tc.cu): device table of the packed tensor-core weights of the blocks
+    std::vector<const float*> tc_table;  // [L][4] filled by genvc_pack_tc
+    bool tc_table_uploaded = false;
+    // Off by default: measured 2.8 ms against 2.4 ms for the per-op prefill replayed as a CUDA graph (48 rows).  Its GEMM
+    // phases run at ~1 us per 32 KB stage even with MMAs, activation loads and weight copies disabled (mbarrier hand-offs
+    // between loader warps and the MMA thread) and every grid barrier costs 2.4-3.6 us (two gpu-scope fences under the
+    // weight stream): profiles/r02b/prefill_fused_phases.txt.  GENVC_FUSED_PREFILL=1 enables it (parity-green).
+    bool use_fused_prefill = false;
 
     // host mirror of the generation state
     int B = 0, P = 0;
@@ -179,6 +187,8 @@ static void plan_workspace(genvc_ctx* c) {
     c->acc_bytes = 2 * (size_t)g.n_layer * D * sizeof(unsigned long long);
     c->o_acc = w.take(c->acc_bytes);
     c->xchg_bytes = w.take(0) - c->o_xchg;
+    c->o_tcptr = w.take((size_t)g.n_layer * 4 * sizeof(const float*));
+    c->o_gbar = w.take(256);
     c->o_splitk = w.take(kSplitKFloats * F);
     const size_t R = c->rows_cap();
     c->o_X = w.take(R * D * F);
@@ -227,6 +237,7 @@ int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
     ctx->layout.build(g);
     if (const char* e = getenv("GENVC_GRAPH")) ctx->use_graphs = e[0] != '0';
     if (const char* e = getenv("GENVC_VW_MIN_TOKENS")) ctx->vw_min_tokens = atoi(e);
+    if (const char* e = getenv("GENVC_FUSED_PREFILL")) ctx->use_fused_prefill = e[0] != '0';
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e == cudaSuccess && device >= 0 && device < ndev) {
@@ -341,9 +352,18 @@ int genvc_pack_tc(genvc_ctx* ctx, float* tc_dev, uint64_t n_floats, void* stream
     DevGuard guard(ctx->device);
     CK(guard.err);
     uint64_t o = 0;
-    for (const TcMat& m : tc_matrices(ctx)) {
+    ctx->tc_table.clear();
+    ctx->tc_table_uploaded = false;
+    const size_t n_block_mats = (size_t)ctx->cfg.n_layer * 4;
+    const std::vector<TcMat> mats = tc_matrices(ctx);
+    // (tc_matrices lists the four matrices of every block first; the table is only valid if none of them was skipped)
+    const bool blocks_complete = mats.size() >= n_block_mats && mats[0].off == ctx->layout.layers[0].attn_w &&
+                                 mats[n_block_mats - 1].off == ctx->layout.layers[ctx->cfg.n_layer - 1].proj2_w;
+    for (size_t i = 0; i < mats.size(); ++i) {
+        const TcMat& m = mats[i];
         CK(gemm_tc_pack(ctx->w(m.off), m.N, m.K, m.ldw, m.w_nk, tc_dev + o, (cudaStream_t)stream));
         ctx->nlaunch += 1;
+        if (blocks_complete && i < n_block_mats) ctx->tc_table.push_back(tc_dev + o);
         o += gemm_tc_packed_floats(m.N, m.K);
     }
     return GENVC_OK;
@@ -357,6 +377,8 @@ int genvc_bind_weights(genvc_ctx* ctx, const float* blob_dev, uint64_t n_floats)
     gemm_tc_forget(blob_dev, blob_dev + ctx->layout.total);
     ctx->blob = blob_dev;
     ctx->stream_packed = false;
+    ctx->tc_table.clear();
+    ctx->tc_table_uploaded = false;
     for (auto& kv : ctx->prefill_graphs)  // captured launches hold the old pointers
         if (kv.second.exec) (void)cudaGraphExecDestroy(kv.second.exec);
     ctx->prefill_graphs.clear();
@@ -670,6 +692,47 @@ int genvc_prefill(genvc_ctx* ctx, const float* prefix_dev, int B, int P, void* s
                              X + (size_t)P * D, (long)M * D, g.n_audio_vocab, ctx->at<int>(ctx->o_flags), st, &ctx->nlaunch));
     // the generation state lives in copy 0 after a prefill (the fused decode launches flip between the two copies)
     ctx->gs_cur = 0;
+    // ---- persistent fused prefill (batch 1, <= 128 rows, tensor-core weights packed): one cooperative launch for the
+    // 30 blocks instead of nine launches per block
+    if (ctx->use_fused_prefill && B == 1 && ctx->tc_table.size() == (size_t)g.n_layer * 4 && ctx->n_sm == ctx->grid &&
+        prefill_fused_supported(D, g.n_head, M, ctx->grid, kSplitKFloats)) {
+        if (!ctx->tc_table_uploaded) {
+            CK(cudaMemcpyAsync(ctx->ws + ctx->o_tcptr, ctx->tc_table.data(), ctx->tc_table.size() * sizeof(const float*),
+                               cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));  // (pageable source; once per weight binding)
+            ctx->tc_table_uploaded = true;
+        }
+        const LayerOff& o0 = L.layers[0];
+        // ln_1 of the first block (the later ones ride in the row-wise reductions of the fused kernel)
+        CK(launch_layernorm(X, D, 0, ctx->at<float>(ctx->o_A), D, 0, M, M, D, ctx->w(o0.ln1_w), ctx->w(o0.ln1_b), nullptr, nullptr,
+                            nullptr, st, &ctx->nlaunch));
+        PrefillFusedArgs fa;
+        fa.L = g.n_layer; fa.D = D; fa.H = g.n_head; fa.M = M; fa.S_max = g.max_seq;
+        fa.blob = ctx->blob;
+        fa.layer_stride = g.n_layer > 1 ? (long long)(L.layers[1].ln1_w - o0.ln1_w) : 0;
+        fa.ln1_w = (long long)o0.ln1_w; fa.ln1_b = (long long)o0.ln1_b; fa.attn_b = (long long)o0.attn_b;
+        fa.proj_b = (long long)o0.proj_b; fa.ln2_w = (long long)o0.ln2_w; fa.ln2_b = (long long)o0.ln2_b;
+        fa.fc_b = (long long)o0.fc_b; fa.proj2_b = (long long)o0.proj2_b;
+        fa.tcw = ctx->at<const float*>(ctx->o_tcptr);
+        fa.X = X; fa.A = ctx->at<float>(ctx->o_A); fa.QKV = ctx->at<float>(ctx->o_QKV); fa.U = ctx->at<float>(ctx->o_U);
+        fa.ws = ctx->at<float>(ctx->o_splitk);
+        fa.kv = ctx->kv; fa.kv_layer_stride = (long long)ctx->kv_plane();
+        fa.gbar = ctx->at<unsigned>(ctx->o_gbar);
+        fa.prof = (ctx->trace != nullptr && ctx->trace_slots >= 16) ? ctx->trace : nullptr;  // debug hook shared with the decode kernels
+        if (const char* e = getenv("GENVC_PREFILL_DBG")) fa.dbg = atoi(e);
+        CK(cudaMemsetAsync(fa.gbar, 0, sizeof(unsigned), st));
+        CK(launch_prefill_fused(fa, ctx->grid, st));
+        ctx->nlaunch += 1;
+        if (int rc = run_head(ctx, B, M, P, nullptr, st)) return rc;
+        CK(launch_init_state(ctx->gstate(0), ctx->gseen(0), B, P, g.n_audio_vocab, ctx->Vpad, g.start_audio, st, &ctx->nlaunch));
+        ctx->B = B;
+        ctx->P = P;
+        ctx->prefilled = true;
+        ctx->pending = true;
+        ctx->vw_filled = false;
+        ctx->n_host = 0;
+        return GENVC_OK;
+    }
     auto body = [&]() -> int {
         if (int rc = run_blocks(ctx, B, M, 0, nullptr, st)) return rc;
         if (int rc = run_head(ctx, B, M, P, nullptr, st)) return rc;

@@ -300,6 +300,531 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(GemmArgs a, const f
     }
 }
 
+// =============================================================================================
+// Persistent fused prefill (batch 1, <= 128 rows): the 30 pre-LN blocks of layers/gpt_inference.py:81-112 in ONE
+// cooperative launch instead of nine launches per block.  Same arithmetic as the per-op path, phase by phase:
+//   QKV GEMM (split-K) | reduce + bias + K/V append | causal attention | attn c_proj GEMM | reduce + residual + ln_2 |
+//   c_fc GEMM | reduce + bias + gelu_new | mlp c_proj GEMM | reduce + residual + ln_1 of the next block
+// separated by grid barriers (one arrival counter; workers only).  What persistence buys: the TMA producer warp walks
+// the weight stream of ALL phases and runs ahead of the barriers / reductions (the ring is always full of the next
+// GEMM's first stages), TMEM / mbarriers are set up once, no launch gaps.
+//   warps 0-7  workers: activation loaders + TMEM epilogue (0-3) during a GEMM phase, all eight in the reduce / attention phases
+//   warp  8    TMA producer (one thread), free-running over the whole kernel
+//   warp  9    MMA issuer (one thread): follows the full barriers; waits for the epilogue of job k before job k+1 reuses TMEM
+// A GEMM phase is one wave: job = (128-column tile, K range) for CTA < tiles x splits, partition as launch_gemm_tc.
+// Everything another CTA wrote is read through L2 (ld.global.cg): L1 is not coherent across a grid barrier.
+// =============================================================================================
+struct PrefillParams {
+    int L, D, H, M, S_max;
+    const float* blob;
+    long long layer_stride;  // floats between the same tensor of consecutive layers
+    long long ln1_w, ln1_b, attn_b, proj_b, ln2_w, ln2_b, fc_b, proj2_b;  // offsets of layer 0 in the blob
+    const float* const* tcw;  // [L][4] packed tensor-core copies: c_attn, attn c_proj, c_fc, mlp c_proj
+    float *X, *A, *QKV, *U, *ws;
+    float* kv;                // K plane of layer l at kv + 2 l stride, V plane at kv + (2 l + 1) stride (batch row 0)
+    long long kv_layer_stride;
+    unsigned* gbar;           // grid-barrier arrival counter, zero at launch
+    unsigned long long* prof; // debug: [grid][16] cycles per phase kind accumulated by thread 0 (null = off)
+    int dbg;                  // debug (results invalid): 1 = no MMAs, 2 = no activation loads, 4 = no weight copies
+};
+
+constexpr int PF_WORKERS = 256, PF_THREADS = 320;
+
+struct PfJob {
+    int has, n0, kb, nst;
+};
+// phase 0..3 = c_attn, attn c_proj, c_fc, mlp c_proj;  partition as launch_gemm_tc (one row chunk)
+__device__ __forceinline__ void pf_shape(int ph, int D, int& N, int& K) {
+    N = ph == 0 ? 3 * D : (ph == 2 ? 4 * D : D);
+    K = ph == 3 ? 4 * D : D;
+}
+__device__ __forceinline__ void pf_split(int N, int K, int& tiles, int& splits, int& k_chunk) {
+    tiles = (N + BN - 1) / BN;
+    splits = 1;
+    if (tiles < 120) {
+        splits = 148 / tiles;
+        splits = min(splits, K / 64);
+        if (splits < 1) splits = 1;
+    }
+    k_chunk = K;
+    if (splits > 1) {
+        k_chunk = ((K + splits - 1) / splits + KT - 1) / KT * KT;
+        splits = (K + k_chunk - 1) / k_chunk;
+    }
+}
+__device__ __forceinline__ PfJob pf_job(int ph, int D, int cta) {
+    int N, K, tiles, splits, k_chunk;
+    pf_shape(ph, D, N, K);
+    pf_split(N, K, tiles, splits, k_chunk);
+    PfJob j;
+    j.has = cta < tiles * splits;
+    const int tile = cta % tiles, z = cta / tiles;
+    j.n0 = tile * BN;
+    j.kb = z * k_chunk;
+    j.nst = j.has ? (min(K, j.kb + k_chunk) - j.kb) / KT : 0;
+    return j;
+}
+
+__device__ __forceinline__ void pf_grid_barrier(unsigned* cnt, unsigned& epoch, int G, int tid) {
+    bar_sync(1, PF_WORKERS);
+    epoch += 1u;
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(cnt, 1u);
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(cnt) < epoch * (unsigned)G) {
+            if (++spins > (1u << 26)) __trap();
+        }
+        __threadfence();
+    }
+    bar_sync(1, PF_WORKERS);
+}
+
+// one (query row, head) per group of four warps: warp w of the group takes keys w, w + 4, ... in trips of four keys (K and V
+// rows of a trip are requested together), online softmax per warp, the four partial states merged through shared memory.
+// q, K, V rows straight from the QKV rows in L2 (coalesced: a row is hd contiguous floats); arithmetic of HF
+// GPT2Attention._attn (scale 1 / sqrt(hd), causal).  sm: [4 warps][hd + 2] floats of the group.
+template <int HD>
+__device__ __forceinline__ void pf_attention_item(const float* __restrict__ QKV, float* __restrict__ O, int D, int i, int h, int lane,
+                                                  int gw, float* sm, int bar_id) {
+    constexpr int DPL = HD / 32;
+    const float scale = 1.0f / sqrtf((float)HD);
+    const size_t rs = 3 * (size_t)D;
+    float q[DPL], o[DPL];
+    auto ldrow = [&](const float* base, float* dst) {
+        if constexpr (DPL >= 4) {
+#pragma unroll
+            for (int c = 0; c < DPL / 4; ++c) {
+                const float4 t = ldcg4(base + lane * DPL + 4 * c);
+                dst[4 * c] = t.x; dst[4 * c + 1] = t.y; dst[4 * c + 2] = t.z; dst[4 * c + 3] = t.w;
+            }
+        } else if constexpr (DPL == 2) {
+            const float2 t = ldcg2(base + lane * 2);
+            dst[0] = t.x; dst[1] = t.y;
+        } else {
+            dst[0] = ldcg(base + lane);
+        }
+    };
+    ldrow(QKV + (size_t)i * rs + h * HD, q);
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) o[d] = 0.0f;
+    float m = -INFINITY, l = 0.0f;
+    constexpr int KPT = DPL >= 8 ? 2 : 4;   // keys per trip (register budget: K and V rows of a trip are both in flight)
+    for (int j0 = gw; j0 <= i; j0 += 4 * KPT) {  // this warp's keys: j0, j0 + 4, ...
+        float k[KPT][DPL], v[KPT][DPL], sc[KPT];
+#pragma unroll
+        for (int u = 0; u < KPT; ++u) {
+            if (j0 + 4 * u <= i) {
+                ldrow(QKV + (size_t)(j0 + 4 * u) * rs + D + h * HD, k[u]);
+                ldrow(QKV + (size_t)(j0 + 4 * u) * rs + 2 * D + h * HD, v[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < KPT; ++u) {
+            sc[u] = 0.0f;
+            if (j0 + 4 * u <= i) {
+#pragma unroll
+                for (int d = 0; d < DPL; ++d) sc[u] = fmaf(q[d], k[u][d], sc[u]);
+            }
+        }
+#pragma unroll
+        for (int x = 16; x > 0; x >>= 1)
+#pragma unroll
+            for (int u = 0; u < KPT; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], x);
+        float mb = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < KPT; ++u) {
+            sc[u] = (j0 + 4 * u <= i) ? sc[u] * scale : -INFINITY;
+            mb = fmaxf(mb, sc[u]);
+        }
+        const float mn = fmaxf(m, mb);
+        const float c = expf(m - mn);  // first trip: exp(-inf) = 0
+        l *= c;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) o[d] *= c;
+#pragma unroll
+        for (int u = 0; u < KPT; ++u) {
+            if (j0 + 4 * u <= i) {
+                const float pj = expf(sc[u] - mn);
+                l += pj;
+#pragma unroll
+                for (int d = 0; d < DPL; ++d) o[d] = fmaf(pj, v[u][d], o[d]);
+            }
+        }
+        m = mn;
+    }
+    // merge the four warp states (a warp without keys has m = -inf, l = 0)
+    float* mine = sm + gw * (HD + 2);
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) mine[lane * DPL + d] = o[d];
+    if (lane == 0) {
+        mine[HD] = m;
+        mine[HD + 1] = l;
+    }
+    if (bar_id == 2) bar_sync(2, 128); else bar_sync(3, 128);
+    if (gw == 0) {
+        float M4 = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) M4 = fmaxf(M4, sm[w * (HD + 2) + HD]);
+        float L4 = 0.0f, acc[DPL];
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) acc[d] = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float mw = sm[w * (HD + 2) + HD];
+            const float cw = (mw == -INFINITY) ? 0.0f : expf(mw - M4);
+            L4 = fmaf(sm[w * (HD + 2) + HD + 1], cw, L4);
+#pragma unroll
+            for (int d = 0; d < DPL; ++d) acc[d] = fmaf(sm[w * (HD + 2) + lane * DPL + d], cw, acc[d]);
+        }
+        const float inv = 1.0f / L4;
+        float* dst = O + (size_t)i * D + h * HD + lane * DPL;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) dst[d] = acc[d] * inv;
+    }
+    if (bar_id == 2) bar_sync(2, 128); else bar_sync(3, 128);  // sm is reused by the group's next item
+}
+
+template <int MP>
+__global__ void __launch_bounds__(PF_THREADS, 1) prefill_fused_kernel(PrefillParams p) {
+    using C = Cfg<MP>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* empty = full + C::STAGES;
+    uint64_t* done = empty + C::STAGES;   // MMAs of a job complete -> epilogue
+    uint64_t* tfree = done + 1;           // epilogue has read TMEM -> the next job may overwrite it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfree + 1);
+    float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [2][8] LayerNorm partials of the row-wise reductions
+    float* att_sm = red + 16;                                // [2 groups][4 warps][256 + 2] attention merge scratch
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x, G = gridDim.x;
+    const int D = p.D, M = p.M, H = p.H, HD = D / H;
+
+    if (tid == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full[s], 4 + 1);  // one arrival per loader warp + the producer's expect_tx arrival
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(done, 1);
+        mbar_init(tfree, 4);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(MP)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ================= weight producer: walks the stream of every GEMM phase of every layer =================
+        if (lane == 0) {
+            const uint64_t policy = l2_policy_evict_first();
+            uint32_t gi = 0;
+            for (int l = 0; l < p.L; ++l) {
+                for (int ph = 0; ph < 4; ++ph) {
+                    const PfJob j = pf_job(ph, D, cta);
+                    if (!j.has) continue;
+                    int N, K;
+                    pf_shape(ph, D, N, K);
+                    const float* src = p.tcw[l * 4 + ph] + ((size_t)(j.n0 / BN) * (K / KT) + j.kb / KT) * W_STAGE_FLOATS;
+                    for (int it = 0; it < j.nst; ++it, ++gi) {
+                        const int s = gi % C::STAGES;
+                        mbar_wait(&empty[s], ((gi / C::STAGES) & 1u) ^ 1u);
+                        if (p.dbg & 4) {
+                            mbar_arrive(&full[s]);
+                        } else {
+                            mbar_arrive_expect_tx(&full[s], (uint32_t)W_STAGE_BYTES);
+                            bulk_g2s_hint(smem + s * C::STAGE_BYTES, src + (size_t)it * W_STAGE_FLOATS, (uint32_t)W_STAGE_BYTES, &full[s], policy);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            uint32_t gi = 0, nj = 0;
+            for (int l = 0; l < p.L; ++l) {
+                for (int ph = 0; ph < 4; ++ph) {
+                    const PfJob j = pf_job(ph, D, cta);
+                    if (!j.has) continue;
+                    if (nj > 0) mbar_wait(tfree, (nj - 1u) & 1u);  // the previous job's accumulator has been read
+                    tc_fence_after();
+                    for (int it = 0; it < j.nst; ++it, ++gi) {
+                        const int s = gi % C::STAGES;
+                        mbar_wait(&full[s], (gi / C::STAGES) & 1u);
+                        tc_fence_after();
+                        const uint32_t sw_hi = smem_u32(smem + s * C::STAGE_BYTES), sw_lo = sw_hi + BN * KT * 4;
+                        const uint32_t sx_hi = sw_hi + W_STAGE_BYTES, sx_lo = sx_hi + C::X_HALF;
+#pragma unroll
+                        for (int q = 0; q < KT / 8; ++q) {
+                            if (p.dbg & 1) break;
+                            const uint32_t ko = (uint32_t)q * 256u;
+                            const uint64_t wh = make_desc(sw_hi + ko), wl = make_desc(sw_lo + ko);
+                            const uint64_t xh = make_desc(sx_hi + ko), xl = make_desc(sx_lo + ko);
+                            mma_tf32(tmem_base, wl, xh, C::IDESC, (it > 0 || q > 0) ? 1u : 0u);
+                            mma_tf32(tmem_base, wh, xl, C::IDESC, 1u);
+                            mma_tf32(tmem_base, wh, xh, C::IDESC, 1u);
+                        }
+                        mma_commit(&empty[s]);
+                    }
+                    mma_commit(done);
+                    ++nj;
+                }
+            }
+        }
+    } else {
+        // ================= workers =================
+        unsigned epoch = 0;
+        uint32_t gi = 0, nj = 0;
+        const float* blob = p.blob;
+        // debug phase profile: [0..3] GEMM phase of c_attn / proj / fc / proj2 (loaders + epilogue), [4] barrier after a GEMM,
+        // [5] flat reduce, [6] row-wise reduce, [7] barrier after a reduce, [8] attention, [9] barrier after attention
+        unsigned long long prof[16];
+        for (int k = 0; k < 16; ++k) prof[k] = 0ull;
+        long long pc = clock64();
+        auto mark = [&](int k) {
+            if (p.prof != nullptr && tid == 0) {
+                const long long c = clock64();
+                prof[k] += (unsigned long long)(c - pc);
+                pc = c;
+            }
+        };
+        for (int l = 0; l < p.L; ++l) {
+            const long long lo = (long long)l * p.layer_stride;
+            float* kc = p.kv + ((size_t)l * 2 + 0) * p.kv_layer_stride;
+            float* vc = p.kv + ((size_t)l * 2 + 1) * p.kv_layer_stride;
+            for (int ph = 0; ph < 4; ++ph) {
+                int N, K, tiles, splits, k_chunk;
+                pf_shape(ph, D, N, K);
+                pf_split(N, K, tiles, splits, k_chunk);
+                const PfJob j = pf_job(ph, D, cta);
+                const float* Ain = ph == 3 ? p.U : p.A;
+                const int lda = ph == 3 ? 4 * D : D;
+                // ---------------- GEMM phase: activation loaders + TMEM epilogue (warps 0-3) ----------------
+                if (j.has && warp < 4) {
+                    constexpr int NQ = MP / 16;
+                    constexpr int PD = MP == 64 ? 3 : 2, NBUF = PD + 1;  // prefetch distance in stages
+                    const int r0 = lane & 7, c = lane >> 3;
+                    float4 va[NBUF][NQ];
+                    auto load_stage = [&](int it, float4* pa) {
+                        const int k0 = j.kb + it * KT;
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+                            const int row = (MP / 4) * warp + 8 * (q >> 1) + r0, kc4 = c + 4 * (q & 1);
+                            pa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (row < M && !(p.dbg & 2)) pa[q] = ldcg4(Ain + (size_t)row * lda + k0 + 4 * kc4);
+                        }
+                    };
+                    auto store_stage = [&](int s, const float4* pa) {
+                        unsigned char* sx_hi = smem + s * C::STAGE_BYTES + W_STAGE_BYTES;
+                        unsigned char* sx_lo = sx_hi + C::X_HALF;
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+                            const int row = (MP / 4) * warp + 8 * (q >> 1) + r0, kc4 = c + 4 * (q & 1);
+                            float4 hi, lo4;
+                            split_tf32(pa[q].x, hi.x, lo4.x);
+                            split_tf32(pa[q].y, hi.y, lo4.y);
+                            split_tf32(pa[q].z, hi.z, lo4.z);
+                            split_tf32(pa[q].w, hi.w, lo4.w);
+                            const uint32_t o = core_off(row, kc4);
+                            *reinterpret_cast<float4*>(sx_hi + o) = hi;
+                            *reinterpret_cast<float4*>(sx_lo + o) = lo4;
+                        }
+                    };
+                    // register ring of NBUF stages: the loads of stages cur + 1 .. cur + PD are in flight while stage cur is split
+                    // and stored (with one stage of lookahead every stage cost a whole L2 round trip: 1.7 us per 32 KB stage)
+                    long long sc0 = clock64();
+#pragma unroll
+                    for (int b = 0; b < PD; ++b)
+                        if (b < j.nst) load_stage(b, va[b]);
+                    for (int it = 0; it < j.nst; it += NBUF) {
+#pragma unroll
+                        for (int hh = 0; hh < NBUF; ++hh) {
+                            const int cur = it + hh;
+                            if (cur < j.nst) {
+                                if (cur + PD < j.nst) load_stage(cur + PD, va[(hh + PD) % NBUF]);
+                                const uint32_t g2 = gi + (uint32_t)cur;
+                                const int s = g2 % C::STAGES;
+                                if (lane == 0) mbar_wait(&empty[s], ((g2 / C::STAGES) & 1u) ^ 1u);
+                                __syncwarp();
+                                if (!(p.dbg & 16)) store_stage(s, va[hh]);
+                                if (!(p.dbg & 8)) fence_async_smem();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&full[s]);
+                            }
+                        }
+                    }
+                    long long sc1 = clock64();
+                    // epilogue: raw split-K partials, lane = output column, register = row
+                    if (lane == 0) mbar_wait(done, nj & 1u);
+                    __syncwarp();
+                    long long sc2 = clock64();
+                    tc_fence_after();
+                    const int n = j.n0 + 32 * warp + lane;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+                    float* out = p.ws + (size_t)(j.kb / k_chunk) * ((size_t)M * N) + n;
+#pragma unroll
+                    for (int hh = 0; hh < MP / 32; ++hh) {
+                        float v[32];
+                        tmem_ld32(taddr + (uint32_t)(32 * hh), v);
+                        if (n < N) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                if (32 * hh + i < M) out[0] = v[i];
+                                out += N;
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tfree);
+                    if (p.prof != nullptr && tid == 0) {
+                        const long long sc3 = clock64();
+                        prof[11] += (unsigned long long)(sc1 - sc0);
+                        prof[12] += (unsigned long long)(sc2 - sc1);
+                        prof[13] += (unsigned long long)(sc3 - sc2);
+                    }
+                }
+                if (j.has) {
+                    gi += (uint32_t)j.nst;
+                    nj += 1u;
+                }
+                mark(ph);
+                pf_grid_barrier(p.gbar, epoch, G, tid);
+                mark(4);
+                // ---------------- reduce phase ----------------
+                const size_t total = (size_t)M * N;
+                if (ph == 0 || ph == 2) {
+                    // flat: sum of the partials in split order + bias (+ gelu_new) -> QKV (+ K/V cache append) | U
+                    const float* bias = blob + (ph == 0 ? p.attn_b : p.fc_b) + lo;
+                    float* Cout = ph == 0 ? p.QKV : p.U;
+                    // (four consecutive outputs per thread; the loads of all splits are issued before the first add: a loop
+                    // of load-add pairs serialises on L2 latency, ~0.7 us per split)
+                    for (size_t i4 = (size_t)cta * PF_WORKERS + tid; i4 < total / 4; i4 += (size_t)G * PF_WORKERS) {
+                        const size_t i = 4 * i4;
+                        const int mrow = (int)(i / N), n = (int)(i % N);
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int z0 = 0; z0 < splits; z0 += 8) {  // eight loads in flight, summed in split order
+                            float4 t[8];
+#pragma unroll
+                            for (int z = 0; z < 8; ++z)
+                                if (z0 + z < splits) t[z] = ldcg4(p.ws + (size_t)(z0 + z) * total + i);
+#pragma unroll
+                            for (int z = 0; z < 8; ++z) {
+                                if (z0 + z < splits) {
+                                    v.x += t[z].x; v.y += t[z].y; v.z += t[z].z; v.w += t[z].w;
+                                }
+                            }
+                        }
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
+                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                        if (ph == 2) {
+                            v.x = gelu_new(v.x); v.y = gelu_new(v.y); v.z = gelu_new(v.z); v.w = gelu_new(v.w);
+                        }
+                        *reinterpret_cast<float4*>(Cout + i) = v;
+                        if (ph == 0 && n >= D) {  // K/V cache append (4 consecutive columns stay inside one head: hd % 4 == 0)
+                            const int cc = (n - D) % D;
+                            float* dst = (n < 2 * D) ? kc : vc;
+                            *reinterpret_cast<float4*>(dst + ((size_t)(cc / HD) * p.S_max + mrow) * HD + (cc % HD)) = v;
+                        }
+                    }
+                } else {
+                    // row-wise: sum + bias + residual -> X (in place), then the LayerNorm that consumes it -> A
+                    const float* bias = blob + (ph == 1 ? p.proj_b : p.proj2_b) + lo;
+                    const bool with_ln = ph == 1 || l + 1 < p.L;
+                    const float* lw = blob + (ph == 1 ? p.ln2_w + lo : p.ln1_w + lo + p.layer_stride);
+                    const float* lb = blob + (ph == 1 ? p.ln2_b + lo : p.ln1_b + lo + p.layer_stride);
+                    for (int row = cta; row < M; row += G) {
+                        const int n = tid * 4;
+                        const bool valid = n < N;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid) {
+                            const float* src = p.ws + (size_t)row * N + n;
+                            for (int z0 = 0; z0 < splits; z0 += 8) {  // eight loads in flight, summed in split order
+                                float4 t[8];
+#pragma unroll
+                                for (int z = 0; z < 8; ++z)
+                                    if (z0 + z < splits) t[z] = ldcg4(src + (size_t)(z0 + z) * total);
+#pragma unroll
+                                for (int z = 0; z < 8; ++z) {
+                                    if (z0 + z < splits) {
+                                        acc.x += t[z].x; acc.y += t[z].y; acc.z += t[z].z; acc.w += t[z].w;
+                                    }
+                                }
+                            }
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
+                            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+                            const float4 r = ldcg4(p.X + (size_t)row * D + n);
+                            acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+                            *reinterpret_cast<float4*>(p.X + (size_t)row * D + n) = acc;
+                        }
+                        float sum = valid ? ((acc.x + acc.y) + (acc.z + acc.w)) : 0.0f;
+                        sum = warp_sum(sum);
+                        if (lane == 0) red[warp] = sum;
+                        bar_sync(1, PF_WORKERS);
+                        float tot = 0.0f;
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) tot += red[w];
+                        const float mean = tot / (float)N;
+                        const float d0 = acc.x - mean, d1 = acc.y - mean, d2 = acc.z - mean, d3 = acc.w - mean;
+                        float q = valid ? (fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3)) : 0.0f;
+                        q = warp_sum(q);
+                        if (lane == 0) red[8 + warp] = q;
+                        bar_sync(1, PF_WORKERS);
+                        float qt = 0.0f;
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) qt += red[8 + w];
+                        const float rstd = 1.0f / sqrtf(qt / (float)N + 1e-5f);
+                        if (valid && with_ln) {
+                            const float4 ww = __ldg(reinterpret_cast<const float4*>(lw + n));
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(lb + n));
+                            *reinterpret_cast<float4*>(p.A + (size_t)row * D + n) =
+                                make_float4(d0 * rstd * ww.x + bb.x, d1 * rstd * ww.y + bb.y, d2 * rstd * ww.z + bb.z, d3 * rstd * ww.w + bb.w);
+                        }
+                        bar_sync(1, PF_WORKERS);  // red[] is rewritten by the next row
+                    }
+                }
+                mark((ph == 0 || ph == 2) ? 5 : 6);
+                pf_grid_barrier(p.gbar, epoch, G, tid);
+                mark(7);
+                // ---------------- causal attention over the rows themselves (after the QKV reduce) ----------------
+                if (ph == 0) {
+                    // two groups of four warps per CTA; items dealt round-robin over the 2 G groups
+                    const int grp = warp >> 2, gw = warp & 3;
+                    float* asm_ = att_sm + grp * 4 * (256 + 2);
+                    for (int item = grp * G + cta; item < M * H; item += 2 * G) {
+                        const int i = item / H, h = item % H;
+                        switch (HD) {
+                            case 32: pf_attention_item<32>(p.QKV, p.A, D, i, h, lane, gw, asm_, 2 + grp); break;
+                            case 64: pf_attention_item<64>(p.QKV, p.A, D, i, h, lane, gw, asm_, 2 + grp); break;
+                            case 128: pf_attention_item<128>(p.QKV, p.A, D, i, h, lane, gw, asm_, 2 + grp); break;
+                            case 256: pf_attention_item<256>(p.QKV, p.A, D, i, h, lane, gw, asm_, 2 + grp); break;
+                            default: break;
+                        }
+                    }
+                    mark(8);
+                    pf_grid_barrier(p.gbar, epoch, G, tid);
+                    mark(9);
+                }
+            }
+        }
+        if (p.prof != nullptr && tid == 0)
+            for (int k = 0; k < 16; ++k) p.prof[(size_t)cta * 16 + k] = prof[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(MP) : "memory");
+    }
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
@@ -307,6 +832,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(GemmArgs a, const f
 // ---------------------------------------------------------------------------------------------
 }  // namespace gv
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -396,6 +922,49 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, float* ws, size_t ws_floats, const
     *splits_out = splits;
     if (MP == 64) return cudaLaunchKernelEx(&cfg, tc::gemm_tc_kernel<64>, a, Wt, ws, k_chunk, skip);
     return cudaLaunchKernelEx(&cfg, tc::gemm_tc_kernel<128>, a, Wt, ws, k_chunk, skip);
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent fused prefill: host launcher
+// ---------------------------------------------------------------------------------------------
+bool prefill_fused_supported(int D, int H, int M, int grid, size_t ws_floats) {
+    if (D % 128 || D > 1024 || M < 16 || M > 128 || grid != 148) return false;  // (the split partition assumes 148 SMs)
+    const int hd = D / H;
+    if (!(hd == 32 || hd == 64 || hd == 128 || hd == 256)) return false;
+    // every GEMM phase must be one wave of split-K jobs whose partials fit the workspace
+    for (int ph = 0; ph < 4; ++ph) {
+        const int N = ph == 0 ? 3 * D : (ph == 2 ? 4 * D : D), K = ph == 3 ? 4 * D : D;
+        const int tiles = (N + tc::BN - 1) / tc::BN;
+        if (tiles >= 120) return false;
+        int splits = std::min(148 / tiles, K / 64);
+        if (splits < 2) return false;
+        const int k_chunk = ((K + splits - 1) / splits + tc::KT - 1) / tc::KT * tc::KT;
+        splits = (K + k_chunk - 1) / k_chunk;
+        if (tiles * splits > grid || (size_t)splits * M * N > ws_floats) return false;
+    }
+    return true;
+}
+
+cudaError_t launch_prefill_fused(const PrefillFusedArgs& a, int grid, cudaStream_t st) {
+    tc::PrefillParams p;
+    p.L = a.L; p.D = a.D; p.H = a.H; p.M = a.M; p.S_max = a.S_max;
+    p.blob = a.blob; p.layer_stride = a.layer_stride;
+    p.ln1_w = a.ln1_w; p.ln1_b = a.ln1_b; p.attn_b = a.attn_b; p.proj_b = a.proj_b;
+    p.ln2_w = a.ln2_w; p.ln2_b = a.ln2_b; p.fc_b = a.fc_b; p.proj2_b = a.proj2_b;
+    p.tcw = a.tcw; p.X = a.X; p.A = a.A; p.QKV = a.QKV; p.U = a.U; p.ws = a.ws;
+    p.kv = a.kv; p.kv_layer_stride = a.kv_layer_stride; p.gbar = a.gbar; p.prof = a.prof; p.dbg = a.dbg;
+    void* args[] = {&p};
+    cudaError_t e;
+    if (a.M <= 64) {
+        const size_t smem = tc::Cfg<64>::SMEM_BYTES + 256 + 2 * 4 * 258 * sizeof(float);
+        e = cudaFuncSetAttribute(tc::prefill_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        return cudaLaunchCooperativeKernel((void*)tc::prefill_fused_kernel<64>, dim3(grid), dim3(tc::PF_THREADS), args, smem, st);
+    }
+    const size_t smem = tc::Cfg<128>::SMEM_BYTES + 256 + 2 * 4 * 258 * sizeof(float);
+    e = cudaFuncSetAttribute(tc::prefill_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaLaunchCooperativeKernel((void*)tc::prefill_fused_kernel<128>, dim3(grid), dim3(tc::PF_THREADS), args, smem, st);
 }
 
 }  // namespace gv

@@ -93,6 +93,22 @@ void gemm_tc_forget(const float* lo, const float* hi);  // drop registrations of
 bool gemm_tc_eligible(const GemmArgs& a);
 cudaError_t launch_gemm_tc(const GemmArgs& a, float* splitk_ws, size_t splitk_ws_floats, const int* skip, cudaStream_t st,
                            int* splits_out);
+// Persistent fused prefill (gemm_tc.cu): the blocks of a batch-1 prefill of <= 128 rows in one cooperative launch.
+struct PrefillFusedArgs {
+    int L, D, H, M, S_max;
+    const float* blob;
+    long long layer_stride;
+    long long ln1_w, ln1_b, attn_b, proj_b, ln2_w, ln2_b, fc_b, proj2_b;  // blob offsets of layer 0
+    const float* const* tcw;  // device array [L][4]: packed tensor-core weights (c_attn, attn c_proj, c_fc, mlp c_proj)
+    float *X, *A, *QKV, *U, *ws;
+    float* kv;
+    long long kv_layer_stride;
+    unsigned* gbar;  // zeroed by the caller before the launch
+    unsigned long long* prof = nullptr;  // debug phase profile [grid][16] (genvc_debug_trace), or null
+    int dbg = 0;                         // debug knobs (results invalid): see gemm_tc.cu
+};
+bool prefill_fused_supported(int D, int H, int M, int grid, size_t ws_floats);
+cudaError_t launch_prefill_fused(const PrefillFusedArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_gemm(const GemmArgs& a, float* splitk_ws, size_t splitk_ws_floats, const int* skip,
                         cudaStream_t st, unsigned long long* nlaunch);
 // rows are addressed as group g = r / rpg, i = r % rpg: X + g * x_gs + i * x_stride
