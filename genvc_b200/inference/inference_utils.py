@@ -9,6 +9,11 @@ What is different from the reference's drivers:
 * ``synthesize_utt(..., reuse_decode_latents=True)`` skips the teacher-forced second pass
   (``inference_utils.py:71-76``): the fused decode kernel already hands out ``final_norm(ln_f(h))`` of every
   generated position, which is what the second pass recomputes (equal up to fp32 rounding, so it is opt-in);
+* ``synthesize_utt(..., batch_segments=True)`` decodes the equal-length segments of the utterance together: the segments
+  are independent given ``cond_latent`` (no GPT state crosses them, ``inference_utils.py:43-77``), so up to 8 of them
+  share one pass of the weight stream per generated token in the batched fused kernel (rows finish independently and are
+  padded with the stop token, as ``layers/stream_generator.py:860-881`` does for a batch); greedy results are identical to
+  the serial loop row for row, sampled results draw from a different random stream;
 * the streaming driver hands every waveform chunk to an optional ``on_chunk`` callback as soon as it exists and
   records first-chunk latency / real-time factor on the model (``last_latency_s``, ``last_rtf``) besides printing
   them like the reference does.
@@ -86,25 +91,48 @@ def _prepare(model, src_wav, tgt_audio, seg_len):
     return src_wav, cond_latent, plan_segments(src_wav.shape[-1], seg, min_len)
 
 
+def _segment_latents(m, cond_latent, codes, gen_rows, reuse_decode_latents):
+    """Latents of the kept (non-stop) tokens of every row of one generate() call -> list of [1, n_b, D]."""
+    B = codes.shape[0]
+    keeps = [(gen_rows[b] != m.gpt.stop_audio_token).nonzero().squeeze(-1) for b in range(B)]
+    if reuse_decode_latents and getattr(m.gpt, "last_latents", None) is not None:
+        # straight from the decode kernel (no second forward)
+        return [m.gpt.last_latents[b][keeps[b]].reshape(1, -1, m.gpt.last_latents.shape[-1]) for b in range(B)]
+    stride = m.config.model_args.gpt_code_stride_len
+    n_max = max(int(k.numel()) for k in keeps)
+    gen = torch.full((B, n_max), m.gpt.stop_audio_token, dtype=gen_rows.dtype, device=gen_rows.device)
+    for b in range(B):
+        gen[b, : keeps[b].numel()] = gen_rows[b][keeps[b]]
+    out_len = torch.tensor([int(k.numel()) * stride for k in keeps], device=m.device)
+    content_len = torch.full((B,), codes.shape[-1], device=m.device)
+    lat = m.gpt(codes, content_len, gen, out_len, cond_latents=cond_latent.expand(B, -1, -1).contiguous(), return_latent=True)
+    return [lat[b: b + 1, : keeps[b].numel()] for b in range(B)]
+
+
 @torch.inference_mode()
-def synthesize_utt(genVC_mdl, src_wav, tgt_audio, seg_len=6.0, reuse_decode_latents: bool = False):
-    """Non-streaming conversion, segments joined at the latent level (inference_utils.py:23-87)."""
+def synthesize_utt(genVC_mdl, src_wav, tgt_audio, seg_len=6.0, reuse_decode_latents: bool = False, batch_segments: bool = False,
+                   max_rows: int = 8):
+    """Non-streaming conversion, segments joined at the latent level (inference_utils.py:23-87).
+    ``batch_segments``: equal-length segments are decoded together, up to ``max_rows`` rows per ``generate`` call."""
     m = genVC_mdl
     src_wav, cond_latent, plan = _prepare(m, src_wav, tgt_audio, seg_len)
-    latents = []
-    for start, end, pad in plan:
-        codes = _content_codes(m, _segment(src_wav, start, end, pad))
-        gen = m.gpt.generate(cond_latent, codes, do_sample=True, num_beams=1, output_attentions=False,
-                             **_sampling_kwargs(m.config))[0]
-        keep = (gen != m.gpt.stop_audio_token).nonzero().squeeze()
-        if reuse_decode_latents and getattr(m.gpt, "last_latents", None) is not None:
-            # latents of the kept positions, straight from the decode kernel (no second forward)
-            latents.append(m.gpt.last_latents[0][keep].reshape(1, -1, m.gpt.last_latents.shape[-1]))
-            continue
-        gen = gen[keep]
-        out_len = torch.tensor([gen.shape[-1] * m.config.model_args.gpt_code_stride_len], device=m.device)
-        content_len = torch.tensor([codes.shape[-1]], device=m.device)
-        latents.append(m.gpt(codes, content_len, gen.unsqueeze(0), out_len, cond_latents=cond_latent, return_latent=True))
+    kw = dict(do_sample=True, num_beams=1, output_attentions=False, **_sampling_kwargs(m.config))
+    all_codes = [_content_codes(m, _segment(src_wav, start, end, pad)) for start, end, pad in plan]
+    latents = [None] * len(plan)
+    if batch_segments:
+        # bucket by code length (the reference batches only equal-length rows: layers/gpt_inference.py:92-96), keep order
+        buckets = {}
+        for i, c in enumerate(all_codes):
+            buckets.setdefault(int(c.shape[-1]), []).append(i)
+        groups = [idx[k: k + max_rows] for idx in buckets.values() for k in range(0, len(idx), max_rows)]
+    else:
+        groups = [[i] for i in range(len(plan))]
+    for grp in groups:
+        codes = torch.cat([all_codes[i] for i in grp], dim=0)
+        cond = cond_latent.expand(len(grp), -1, -1).contiguous()
+        gen = m.gpt.generate(cond, codes, **kw)
+        for i, lat in zip(grp, _segment_latents(m, cond_latent, codes, gen, reuse_decode_latents)):
+            latents[i] = lat
     return _vocode(m, torch.cat(latents, dim=1))[0].squeeze()
 
 
