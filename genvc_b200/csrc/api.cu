@@ -83,6 +83,7 @@ struct genvc_ctx {
     };
     std::map<std::pair<int, int>, PrefillGraph> prefill_graphs;
     bool use_graphs = true;
+    bool pc_attention_tc = true;  // perceiver cross-attention on tcgen05 (GENVC_PC_TC=0: CUDA-core attention kernel)
     // persistent fused prefill (gemm_tc.cu): device table of the packed tensor-core weights of the blocks
     std::vector<const float*> tc_table;  // [L][4] filled by genvc_pack_tc
     bool tc_table_uploaded = false;
@@ -198,7 +199,7 @@ static void plan_workspace(genvc_ctx* c) {
     // perceiver
     const size_t S = g.max_mel_frames, NL = g.pc_latents, inner = (size_t)g.pc_dim_head * g.pc_heads;
     const size_t Rc = MB * (NL + S);
-    c->o_pc_melT = w.take(MB * S * g.pc_dim_context * F);
+    c->o_pc_melT = w.take(MB * S * c->layout.pc_ctx_pad * F);
     c->o_pc_ctx = w.take(Rc * D * F);
     c->o_pc_kv = w.take(Rc * 2 * inner * F);
     c->o_pc_lat = w.take(MB * NL * D * F);
@@ -236,6 +237,7 @@ int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
         return bad("start/stop audio token outside the vocabulary");
     ctx->layout.build(g);
     if (const char* e = getenv("GENVC_GRAPH")) ctx->use_graphs = e[0] != '0';
+    if (const char* e = getenv("GENVC_PC_TC")) ctx->pc_attention_tc = e[0] != '0';
     if (const char* e = getenv("GENVC_VW_MIN_TOKENS")) ctx->vw_min_tokens = atoi(e);
     if (const char* e = getenv("GENVC_FUSED_PREFILL")) ctx->use_fused_prefill = e[0] != '0';
     int ndev = 0;
@@ -325,11 +327,14 @@ static std::vector<TcMat> tc_matrices(const genvc_ctx* c) {
         v.push_back({o.fc_w, 4 * D, D, 4 * D, 0});
         v.push_back({o.proj2_w, D, 4 * D, D, 0});
     }
+    const int ffp = (int)c->layout.pc_ff_inner_pad, cp = (int)c->layout.pc_ctx_pad;
+    v.push_back({c->layout.pc_proj_w, D, cp, cp, 1});  // proj_context: K = 80 zero-padded to 96
     for (const PcLayerOff& o : c->layout.pc_layers) {
         v.push_back({o.to_q, inner, D, D, 1});
         v.push_back({o.to_kv, 2 * inner, D, D, 1});
         v.push_back({o.to_out, D, inner, inner, 1});
         v.push_back({o.ff0_w, 2 * ffi, D, D, 1});
+        v.push_back({o.ff2_w, D, ffp, ffp, 1});        // FF 2: K = 2730 zero-padded to 2752
     }
     std::vector<TcMat> ok;
     for (const TcMat& m : v)
@@ -619,10 +624,11 @@ int genvc_perceiver(genvc_ctx* ctx, const float* mel_dev, int B, int S_mel, floa
     float* sk = ctx->at<float>(ctx->o_splitk);
     unsigned long long* nl = &ctx->nlaunch;
 
-    CK(launch_transpose_mel(mel_dev, B, C, S_mel, melT, st, nl));
+    const int Cp = (int)L.pc_ctx_pad;  // mel channels zero-padded to the k granularity of the tensor-core GEMM
+    CK(launch_transpose_mel(mel_dev, B, C, Cp, S_mel, melT, st, nl));
     for (int b = 0; b < B; ++b)  // proj_context into rows NL.. of this element's context block
-        CK(launch_gemm(gemm(melT + (size_t)b * S_mel * C, C, ctx->w(L.pc_proj_w), C, 1, ctx->w(L.pc_proj_b), nullptr, 0,
-                            cx + ((size_t)b * RC + NL) * D, D, S_mel, D, C, ACT_NONE),
+        CK(launch_gemm(gemm(melT + (size_t)b * S_mel * Cp, Cp, ctx->w(L.pc_proj_w), Cp, 1, ctx->w(L.pc_proj_b), nullptr, 0,
+                            cx + ((size_t)b * RC + NL) * D, D, S_mel, D, Cp, ACT_NONE),
                        sk, kSplitKFloats, nullptr, st, nl));
     CK(launch_copy_rows(ctx->w(L.pc_latents), 0, lat, (long)NL * D, B, (long)NL * D, st, nl));  // repeat(latents)
     for (int i = 0; i < g.pc_depth; ++i) {
@@ -632,14 +638,20 @@ int genvc_perceiver(genvc_ctx* ctx, const float* mel_dev, int B, int S_mel, floa
                        kSplitKFloats, nullptr, st, nl));
         CK(launch_gemm(gemm(cx, D, ctx->w(o.to_kv), D, 1, nullptr, nullptr, 0, kvb, 2 * inner, B * RC, 2 * inner, D, ACT_NONE), sk,
                        kSplitKFloats, nullptr, st, nl));
-        AttnArgs a;
-        a.Q = q;           a.q_bs = (long)NL * inner;     a.q_rs = inner;     a.q_hs = g.pc_dim_head;
-        a.K = kvb;         a.k_bs = (long)RC * 2 * inner; a.k_rs = 2 * inner; a.k_hs = g.pc_dim_head;
-        a.V = kvb + inner; a.v_bs = (long)RC * 2 * inner; a.v_rs = 2 * inner; a.v_hs = g.pc_dim_head;
-        a.O = ob;          a.o_bs = (long)NL * inner;     a.o_rs = inner;     a.o_hs = g.pc_dim_head;
-        a.B = B; a.H = g.pc_heads; a.M = NL; a.hd = g.pc_dim_head; a.n_keys = RC; a.causal = 0; a.pos0 = 0;
-        a.scale = 1.0f / sqrtf((float)g.pc_dim_head);
-        CK(launch_attention(a, nullptr, st, nl));
+        if (ctx->pc_attention_tc && pc_attention_tc_supported(NL, g.pc_dim_head, RC)) {
+            // cross-attention on the tensor cores: scores, softmax and P.V of one (element, head) stay on one SM
+            CK(launch_pc_attention_tc(q, kvb, ob, B, g.pc_heads, RC, st));
+            ctx->nlaunch += 1;
+        } else {
+            AttnArgs a;
+            a.Q = q;           a.q_bs = (long)NL * inner;     a.q_rs = inner;     a.q_hs = g.pc_dim_head;
+            a.K = kvb;         a.k_bs = (long)RC * 2 * inner; a.k_rs = 2 * inner; a.k_hs = g.pc_dim_head;
+            a.V = kvb + inner; a.v_bs = (long)RC * 2 * inner; a.v_rs = 2 * inner; a.v_hs = g.pc_dim_head;
+            a.O = ob;          a.o_bs = (long)NL * inner;     a.o_rs = inner;     a.o_hs = g.pc_dim_head;
+            a.B = B; a.H = g.pc_heads; a.M = NL; a.hd = g.pc_dim_head; a.n_keys = RC; a.causal = 0; a.pos0 = 0;
+            a.scale = 1.0f / sqrtf((float)g.pc_dim_head);
+            CK(launch_attention(a, nullptr, st, nl));
+        }
         CK(launch_gemm(gemm(ob, inner, ctx->w(o.to_out), inner, 1, nullptr, lat, D, lat, D, B * NL, D, inner, ACT_NONE), sk,
                        kSplitKFloats, nullptr, st, nl));
         CK(launch_gemm(gemm(lat, D, ctx->w(o.ff0_w), D, 1, ctx->w(o.ff0_b), nullptr, 0, hb, 2 * ffi, B * NL, 2 * ffi, D, ACT_NONE),

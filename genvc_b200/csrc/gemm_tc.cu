@@ -301,6 +301,221 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(GemmArgs a, const f
 }
 
 // =============================================================================================
+// Perceiver cross-attention on tensor cores (layers/perceiver_encoder.py:108-151, Attend: softmax(q k^T / sqrt(64)) v, no
+// mask): one CTA per (batch element, head); 32 latent queries against the 32 + S context keys, head dim 64.
+//   pass 1  scores: per tile of 128 keys,  S^T[128 keys x 32 queries] = K_tile[128 x 64] . Q^T   (tcgen05, M = 128, N = 32,
+//           3xTF32, accumulator in TMEM) -> tcgen05.ld (lane = key) -> scaled scores to shared memory, S[query][key]
+//   softmax rows of S in shared memory (fp32, one warp per 8 queries)
+//   pass 2  per tile of 64 keys,  O^T[64 dims (+64 zero rows) x 32 queries] += V^T_tile[128 x 64 keys] . P_tile^T
+//           accumulated in TMEM over the tiles -> tcgen05.ld (lane = dim) -> out[query][dim]
+// Operands are staged by the threads (fp32 -> TF32 hi | lo, UMMA canonical K-major no-swizzle core matrices), handed to the
+// async proxy with fence.proxy.async; one thread issues the MMAs, tcgen05.commit -> mbarrier tells the CTA when a tile is done.
+// The work is tiny (80 MFLOP per call) and latency-bound; what the kernel buys is that scores and probabilities never
+// leave the SM, and the tensor pipe does the 3xTF32 contractions.
+// =============================================================================================
+constexpr int PA_Q = 32, PA_HD = 64, PA_THREADS = 128;
+
+// byte offset of (row, 16-byte k chunk) in a canonical K-major tile whose rows hold `kchunks` chunks
+__device__ __forceinline__ uint32_t canon_off(int row, int kc, int kchunks) {
+    return (uint32_t)(((row >> 3) * kchunks + kc) * 128 + (row & 7) * 16);
+}
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr, int kchunks) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+    d |= (uint64_t)(128u >> 4) << 16;                        // LBO: between the two 16-byte K chunks of a k-step
+    d |= (uint64_t)(((uint32_t)kchunks * 128u) >> 4) << 32;  // SBO: between 8-row groups
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+constexpr uint32_t PA_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(PA_Q >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__host__ __device__ inline int pa_sp(int RC) { return (RC + 127) / 128 * 128 + 4; }  // row pitch of S (floats)
+__host__ __device__ inline size_t pa_smem_bytes(int RC) {
+    return 1024 /* align */ + 2 * PA_Q * PA_HD * 4 /* Q hi|lo */ + 2 * 128 * 64 * 4 /* tile hi|lo */ + 2 * PA_Q * 64 * 4 /* P tile hi|lo */ +
+           (size_t)PA_Q * pa_sp(RC) * 4 + 64;
+}
+
+__global__ void __launch_bounds__(PA_THREADS, 1) pc_attention_tc_kernel(const float* __restrict__ Q, const float* __restrict__ KV,
+                                                                        float* __restrict__ O, int RC, int inner, float scale) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* q_hi = smem;                              // [32 x 64] canonical, 16 chunks per row
+    unsigned char* q_lo = q_hi + PA_Q * PA_HD * 4;
+    unsigned char* t_hi = q_lo + PA_Q * PA_HD * 4;           // [128 x 64] canonical: K tile (pass 1) | V^T tile (pass 2)
+    unsigned char* t_lo = t_hi + 128 * 64 * 4;
+    unsigned char* p_hi = t_lo + 128 * 64 * 4;               // [32 x 64 keys] canonical: probabilities of the tile
+    unsigned char* p_lo = p_hi + PA_Q * 64 * 4;
+    float* S = reinterpret_cast<float*>(p_lo + PA_Q * 64 * 4);
+    const int SP = pa_sp(RC);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(S + (size_t)PA_Q * SP);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const float* Qb = Q + (size_t)b * PA_Q * inner + h * PA_HD;           // row stride inner
+    const float* Kb = KV + (size_t)b * RC * 2 * inner + h * PA_HD;        // row stride 2 inner
+    const float* Vb = Kb + inner;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // Q -> canonical hi | lo: 32 rows x 16 chunks = 512 chunks, 4 per thread
+    for (int c = tid; c < PA_Q * 16; c += PA_THREADS) {
+        const int row = c >> 4, kc = c & 15;
+        const float4 x = *reinterpret_cast<const float4*>(Qb + (size_t)row * inner + 4 * kc);
+        float4 hi, lo;
+        split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+        const uint32_t o = canon_off(row, kc, 16);
+        *reinterpret_cast<float4*>(q_hi + o) = hi;
+        *reinterpret_cast<float4*>(q_lo + o) = lo;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    uint32_t phase = 0;
+
+    // ---------------- pass 1: scores ----------------
+    const int n1 = (RC + 127) / 128;
+    for (int t = 0; t < n1; ++t) {
+        const int key = t * 128 + tid;  // this thread stages row `tid` of the tile
+        {
+            const float* src = Kb + (size_t)key * 2 * inner;
+#pragma unroll
+            for (int kc = 0; kc < 16; ++kc) {
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (key < RC) x = *reinterpret_cast<const float4*>(src + 4 * kc);
+                float4 hi, lo;
+                split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+                const uint32_t o = canon_off(tid, kc, 16);
+                *reinterpret_cast<float4*>(t_hi + o) = hi;
+                *reinterpret_cast<float4*>(t_lo + o) = lo;
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < PA_HD / 8; ++j) {
+                const uint32_t ko = (uint32_t)j * 256u;
+                const uint64_t ah = make_desc_k(smem_u32(t_hi) + ko, 16), al = make_desc_k(smem_u32(t_lo) + ko, 16);
+                const uint64_t bh = make_desc_k(smem_u32(q_hi) + ko, 16), bl = make_desc_k(smem_u32(q_lo) + ko, 16);
+                mma_tf32(tmem, al, bh, PA_IDESC, j > 0 ? 1u : 0u);
+                mma_tf32(tmem, ah, bl, PA_IDESC, 1u);
+                mma_tf32(tmem, ah, bh, PA_IDESC, 1u);
+            }
+            mma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16), v);  // lane = key of the tile, v[q] = its score with query q
+        if (key < RC) {
+#pragma unroll
+            for (int q = 0; q < PA_Q; ++q) S[(size_t)q * SP + key] = v[q] * scale;
+        }
+        tc_fence_before();
+        __syncthreads();  // the tile buffer and the accumulator are reused
+    }
+    // ---------------- softmax over the keys (rows of S), probabilities in place; zero the padding ----------------
+    const int RCP = (RC + 63) / 64 * 64;
+    for (int q = warp * 8; q < warp * 8 + 8; ++q) {
+        float* row = S + (size_t)q * SP;
+        float m = -INFINITY;
+        for (int j = lane; j < RC; j += 32) m = fmaxf(m, row[j]);
+        m = warp_max(m);
+        float sum = 0.0f;
+        for (int j = lane; j < RC; j += 32) {
+            const float e = expf(row[j] - m);
+            row[j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int j = lane; j < RCP; j += 32) row[j] = j < RC ? row[j] * inv : 0.0f;
+    }
+    // rows 64 .. 127 of the A tile are zero in pass 2 (64 real dims)
+    for (int c = tid; c < 64 * 16; c += PA_THREADS) {
+        const uint32_t o = canon_off(64 + (c >> 4), c & 15, 16);
+        *reinterpret_cast<float4*>(t_hi + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(t_lo + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    // ---------------- pass 2: O^T = V^T . P^T over tiles of 64 keys ----------------
+    const int n2 = RCP / 64;
+    for (int t = 0; t < n2; ++t) {
+        {   // V^T tile: thread = (key tid % 64, dims [32 (tid / 64), +32)): element (dim d, key k) at chunk k / 4, lane k % 4
+            const int k = tid & 63, d0 = (tid >> 6) * 32;
+            const int key = t * 64 + k;
+            const float* src = Vb + (size_t)key * 2 * inner + d0;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (key < RC) x = *reinterpret_cast<const float4*>(src + 4 * c4);
+                const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float hi, lo;
+                    split_tf32(xs[e], hi, lo);
+                    const uint32_t o = canon_off(d0 + 4 * c4 + e, k >> 2, 16) + (uint32_t)(k & 3) * 4u;
+                    *reinterpret_cast<float*>(t_hi + o) = hi;
+                    *reinterpret_cast<float*>(t_lo + o) = lo;
+                }
+            }
+        }
+        // P tile: 32 queries x 16 chunks of 4 keys
+        for (int c = tid; c < PA_Q * 16; c += PA_THREADS) {
+            const int q = c >> 4, kc = c & 15;
+            const float4 x = *reinterpret_cast<const float4*>(S + (size_t)q * SP + t * 64 + 4 * kc);
+            float4 hi, lo;
+            split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+            const uint32_t o = canon_off(q, kc, 16);
+            *reinterpret_cast<float4*>(p_hi + o) = hi;
+            *reinterpret_cast<float4*>(p_lo + o) = lo;
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 64 / 8; ++j) {
+                const uint32_t ko = (uint32_t)j * 256u;
+                const uint64_t ah = make_desc_k(smem_u32(t_hi) + ko, 16), al = make_desc_k(smem_u32(t_lo) + ko, 16);
+                const uint64_t bh = make_desc_k(smem_u32(p_hi) + ko, 16), bl = make_desc_k(smem_u32(p_lo) + ko, 16);
+                mma_tf32(tmem, al, bh, PA_IDESC, (t > 0 || j > 0) ? 1u : 0u);
+                mma_tf32(tmem, ah, bl, PA_IDESC, 1u);
+                mma_tf32(tmem, ah, bh, PA_IDESC, 1u);
+            }
+            mma_commit(bar);
+        }
+        mbar_wait(bar, phase);  // the operands may be overwritten (and, after the last tile, the accumulator read)
+        phase ^= 1u;
+        tc_fence_after();
+        __syncthreads();
+    }
+    if (warp < 2) {  // lanes 0 .. 63 of the accumulator = the 64 output dims
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16), v);
+        float* dst = O + (size_t)b * PA_Q * inner + h * PA_HD + 32 * warp + lane;
+#pragma unroll
+        for (int q = 0; q < PA_Q; ++q) dst[(size_t)q * inner] = v[q];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32) : "memory");
+    }
+}
+
+// =============================================================================================
 // Persistent fused prefill (batch 1, <= 128 rows): the 30 pre-LN blocks of layers/gpt_inference.py:81-112 in ONE
 // cooperative launch instead of nine launches per block.  Same arithmetic as the per-op path, phase by phase:
 //   QKV GEMM (split-K) | reduce + bias + K/V append | causal attention | attn c_proj GEMM | reduce + residual + ln_2 |
@@ -927,6 +1142,18 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, float* ws, size_t ws_floats, const
 // ---------------------------------------------------------------------------------------------
 // persistent fused prefill: host launcher
 // ---------------------------------------------------------------------------------------------
+bool pc_attention_tc_supported(int n_latents, int hd, int RC) {
+    return n_latents == tc::PA_Q && hd == tc::PA_HD && RC >= 1 && tc::pa_smem_bytes(RC) <= 227 * 1024;
+}
+// Q [B, 32, inner], KV [B, RC, 2 inner] (k | v), O [B, 32, inner]; heads = inner / 64
+cudaError_t launch_pc_attention_tc(const float* Q, const float* KV, float* O, int B, int heads, int RC, cudaStream_t st) {
+    const size_t smem = tc::pa_smem_bytes(RC);
+    cudaError_t e = cudaFuncSetAttribute(tc::pc_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tc::pc_attention_tc_kernel<<<dim3(heads, B), tc::PA_THREADS, smem, st>>>(Q, KV, O, RC, heads * tc::PA_HD, 1.0f / sqrtf((float)tc::PA_HD));
+    return cudaGetLastError();
+}
+
 bool prefill_fused_supported(int D, int H, int M, int grid, size_t ws_floats) {
     if (D % 128 || D > 1024 || M < 16 || M > 128 || grid != 148) return false;  // (the split partition assumes 148 SMs)
     const int hd = D / H;

@@ -36,7 +36,8 @@ struct Layout {
     uint64_t text_emb, mel_emb, mel_pos, text_pos, lnf_w, lnf_b, fn_w, fn_b, mel_head_w, mel_head_b, text_head_w,
         text_head_b;
     uint64_t pc_latents, pc_proj_w, pc_proj_b, pc_gamma;
-    uint64_t pc_ff_inner_pad;
+    uint64_t pc_ff_inner_pad;  // row stride of ff.2.weight: inner padded to a multiple of 32 (k granularity of the tcgen05 GEMM)
+    uint64_t pc_ctx_pad;       // row stride of proj_context.weight: dim_context (80) padded to a multiple of 32
     uint64_t total = 0;
 
     uint64_t add(const std::string& name, uint64_t rows, uint64_t cols, uint64_t stride = 0, bool align = true) {
@@ -84,9 +85,10 @@ struct Layout {
         const std::string pc = "conditioning_perceiver.";
         const uint64_t inner = (uint64_t)c.pc_dim_head * c.pc_heads;
         const uint64_t ffi = c.pc_ff_inner;
-        pc_ff_inner_pad = (ffi + 3) & ~uint64_t(3);
+        pc_ff_inner_pad = (ffi + 31) & ~uint64_t(31);
+        pc_ctx_pad = ((uint64_t)c.pc_dim_context + 31) & ~uint64_t(31);
         pc_latents = add(pc + "latents", c.pc_latents, D);
-        pc_proj_w = add(pc + "proj_context.weight", D, c.pc_dim_context);
+        pc_proj_w = add(pc + "proj_context.weight", D, c.pc_dim_context, pc_ctx_pad);
         pc_proj_b = add(pc + "proj_context.bias", 1, D);
         pc_layers.resize(c.pc_depth);
         for (int i = 0; i < c.pc_depth; ++i) {

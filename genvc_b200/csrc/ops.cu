@@ -642,12 +642,13 @@ cudaError_t launch_copy_rows(const float* src, long src_bs, float* dst, long dst
 }
 
 // mel [B,C,S] -> [B,S,C]  (cond_input.permute(0,2,1), layers/gpt.py:369)
-__global__ void transpose_mel_kernel(const float* __restrict__ mel, int C, int S, float* __restrict__ out) {
+// mel [B, C, S] -> out [B, S, Cp] (Cp >= C: row pitch padded with zeros to the k granularity of the tensor-core GEMM)
+__global__ void transpose_mel_kernel(const float* __restrict__ mel, int C, int Cp, int S, float* __restrict__ out) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int s0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const float* src = mel + (size_t)b * C * S;
-    float* dst = out + (size_t)b * C * S;
+    float* dst = out + (size_t)b * Cp * S;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int c = c0 + r, s = s0 + threadIdx.x;
         tile[r][threadIdx.x] = (c < C && s < S) ? src[(size_t)c * S + s] : 0.0f;
@@ -655,13 +656,13 @@ __global__ void transpose_mel_kernel(const float* __restrict__ mel, int C, int S
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int s = s0 + r, c = c0 + threadIdx.x;
-        if (s < S && c < C) dst[(size_t)s * C + c] = tile[threadIdx.x][r];
+        if (s < S && c < Cp) dst[(size_t)s * Cp + c] = tile[threadIdx.x][r];  // (columns C .. Cp-1 were loaded as zeros)
     }
 }
-cudaError_t launch_transpose_mel(const float* mel, int B, int C, int S, float* out, cudaStream_t st,
+cudaError_t launch_transpose_mel(const float* mel, int B, int C, int Cp, int S, float* out, cudaStream_t st,
                                  unsigned long long* nlaunch) {
-    dim3 grid((S + 31) / 32, (C + 31) / 32, B);
-    transpose_mel_kernel<<<grid, dim3(32, 8), 0, st>>>(mel, C, S, out);
+    dim3 grid((S + 31) / 32, (Cp + 31) / 32, B);
+    transpose_mel_kernel<<<grid, dim3(32, 8), 0, st>>>(mel, C, Cp, S, out);
     GV_BUMP(nlaunch);
     return cudaGetLastError();
 }

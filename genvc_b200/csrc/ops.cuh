@@ -107,6 +107,9 @@ struct PrefillFusedArgs {
     unsigned long long* prof = nullptr;  // debug phase profile [grid][16] (genvc_debug_trace), or null
     int dbg = 0;                         // debug knobs (results invalid): see gemm_tc.cu
 };
+// Perceiver cross-attention on tcgen05 (gemm_tc.cu): 32 latent queries, head dim 64, RC = 32 + S context keys.
+bool pc_attention_tc_supported(int n_latents, int hd, int RC);
+cudaError_t launch_pc_attention_tc(const float* Q, const float* KV, float* O, int B, int heads, int RC, cudaStream_t st);
 bool prefill_fused_supported(int D, int H, int M, int grid, size_t ws_floats);
 cudaError_t launch_prefill_fused(const PrefillFusedArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_gemm(const GemmArgs& a, float* splitk_ws, size_t splitk_ws_floats, const int* skip,
@@ -132,7 +135,7 @@ cudaError_t launch_embed_last_token(const GenState* stt, int B, int pos, int D, 
                                     float* out, cudaStream_t st, unsigned long long* nlaunch);
 cudaError_t launch_copy_rows(const float* src, long src_bs, float* dst, long dst_bs, int B, long row_floats, cudaStream_t st,
                              unsigned long long* nlaunch);
-cudaError_t launch_transpose_mel(const float* mel, int B, int C, int S, float* out, cudaStream_t st,
+cudaError_t launch_transpose_mel(const float* mel, int B, int C, int Cp, int S, float* out, cudaStream_t st,
                                  unsigned long long* nlaunch);
 cudaError_t launch_geglu(const float* h, int rows, int inner, int inner_pad, float* out, cudaStream_t st,
                          unsigned long long* nlaunch);
