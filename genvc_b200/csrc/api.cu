@@ -257,7 +257,7 @@ int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
     const int nxv = g.d_model / 128;
     ctx->mega_ok = (nxv == 1 || nxv == 2 || nxv == 4 || nxv == 8) && ceil_div(4 * g.d_model, ctx->grid) <= 32 &&
                    ceil_div(g.n_audio_vocab, ctx->grid) <= 32 && g.n_audio_vocab <= 2048 && g.n_head * 8 <= ctx->grid &&
-                   g.d_model / 8 <= ctx->grid && ctx->grid <= 304 &&
+                   g.d_model / 8 <= ctx->grid && ctx->grid >= 128 && ctx->grid <= 304 &&
                    mega_smem_bytes(g.d_model, (g.n_audio_vocab + 15) / 16 * 16) <= 232448 &&
                    (uint64_t)g.max_gen_mel_tokens * ((uint64_t)GV_TAGS_PER_LAYER * g.n_layer + 1ull) < 0x7FFFFFFFull;
     // batched fused kernel (decode_batch.cu): rows * H attention items must fit the grid (checked per call), the
@@ -486,6 +486,14 @@ int genvc_debug_tune(genvc_ctx* ctx, int window, int nosync, int l2_ahead_tiles,
         ctx->hop_hold = hop_hold;
     }
     ctx->dbg_nosync = nosync ? 1 : 0;
+    return GENVC_OK;
+}
+
+int genvc_debug_layout(const genvc_ctx* ctx, uint64_t* out, int n) {
+    if (!ctx || !out || n < 12) return GENVC_E_INVALID;
+    const uint64_t v[12] = {ctx->o_xq, ctx->o_matt_o, ctx->o_matt_ml, ctx->o_x1, ctx->o_pp, ctx->o_x2, ctx->o_lg, ctx->o_hops,
+                            ctx->o_sbuf, (uint64_t)ctx->grid, (uint64_t)GV_HOP_STRIDE, (uint64_t)HC_COUNT};
+    for (int i = 0; i < 12; ++i) out[i] = v[i];
     return GENVC_OK;
 }
 

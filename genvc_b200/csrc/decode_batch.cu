@@ -217,7 +217,7 @@ __device__ __forceinline__ void load_rows(const float* buf, uint32_t tag, float*
                 const float* p = buf + 2 * ((size_t)(r0 + q) * D + 4 * tid);
                 uint32_t spins = 0;
                 while (!(tags_ok(a[q], tag, 0xffffffffu) && tags_ok(b[q], tag, 0xffffffffu))) {
-                    if (++spins > MEGA_SPIN_LIMIT) __trap();
+                    GV_SPIN(spins, __LINE__, 0u, 0u);
                     a[q] = ld_x16(p);
                     b[q] = ld_x16(p + 4);
                 }
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
                                 const unsigned* cnt = p.att_cnt + (size_t)rh * GV_ATTCNT_STRIDE;
                                 uint32_t spins = 0;
                                 while (ld_relaxed_u32(cnt) < t_cnt + (unsigned)(nsplit - 1)) {
-                                    if (++spins > MEGA_SPIN_LIMIT) __trap();
+                                    GV_SPIN(spins, __LINE__, 0u, 0u);
                                 }
                             }
                             bar_sync(1, MEGA_CONSUMERS);
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
                                             const int it = rh * nsplit + s0 + q;
                                             uint32_t spins = 0;
                                             while (!(tags_ok(a[q], tga, tmask) && b[q].y == tga)) {
-                                                if (++spins > MEGA_SPIN_LIMIT) __trap();
+                                                GV_SPIN(spins, __LINE__, 0u, 0u);
                                                 a[q] = ld_x16(p.att_ml + 2 * (size_t)(it * 2));
                                                 b[q] = ld_x8(p.att_o + 2 * (size_t)(it * HD + tid));
                                             }
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
                                 if (s0 + 8 * k < G) {
                                     uint32_t spins = 0;
                                     while (!tags_ok(v[k], tgp, tmask)) {
-                                        if (++spins > MEGA_SPIN_LIMIT) __trap();
+                                        GV_SPIN(spins, __LINE__, 0u, 0u);
                                         v[k] = ld_x16(src + (size_t)(s0 + 8 * k) * sstride);
                                     }
                                     acc0 += __uint_as_float(v[k].x);

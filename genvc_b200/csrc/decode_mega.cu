@@ -36,6 +36,17 @@
 // No tensor cores: at M = 1 there is no reuse to feed them; fp32 keeps greedy parity.
 #define GV_RING_NSLOT GV_MEGA_NSLOT
 #define GV_MEGA_NS mega1
+#define GV_UNIFORM_TILE_WAIT 1
+// weight loads of a phase hoisted above the hop that delivers its activations (gemv_preload / gemv_finish); switchable for A/B
+#ifndef GV_PRE_QKV
+#define GV_PRE_QKV 1
+#endif
+#ifndef GV_PRE_PROJ
+#define GV_PRE_PROJ 1
+#endif
+#ifndef GV_PRE_HEAD
+#define GV_PRE_HEAD 1
+#endif
 #include "mega_dev.cuh"
 
 namespace gv {
@@ -123,6 +134,18 @@ __device__ __forceinline__ float ld_cg_early(const float* p) {
 // `fill_n` > 0 (first forward after a prefill): the projected values of the fill_n cached positions are computed here
 // too, while this CTA's attn c_proj columns are in shared memory anyway -- warp w takes positions w, w + 8, ..., all
 // units, values straight from the V cache (vfill: [H][S_max][hd]), results to out_fill[(pos H + h) 8 + unit].
+#ifdef GV_PROG
+// debug: per-warp progress markers (tools/hang_dump.py reads them from a side stream while a launch is stuck)
+__device__ unsigned g_prog[160 * 8 * 4];
+#define GV_MARK(code) do { if ((threadIdx.x & 31) == 0) { unsigned* g_ = g_prog + (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4; g_[0] = (code); g_[1] = (unsigned)lc; if ((code) == 1u) g_[2] = nbar; g_[3] = nbar; } } while (0)
+#define GV_NBAR(k) (nbar += (k))
+__device__ unsigned g_progt[160 * 256];
+#define GV_MARKT(code) do { g_progt[blockIdx.x * 256 + threadIdx.x] = ((unsigned)lc << 8) | (code); } while (0)
+#else
+#define GV_MARK(code) do { } while (0)
+#define GV_MARKT(code) do { } while (0)
+#define GV_NBAR(k) do { } while (0)
+#endif
 template <int NXV, int HD, class Epi, class Bias>
 __device__ __forceinline__ void gemv_heads(const Ring& ring, const Cons& cs, int nunits, const float* xs, int warp, int lane, Epi epi,
                                            Bias bias, int fill_n, const float* vfill, int S_max, float* out_fill) {
@@ -131,7 +154,7 @@ __device__ __forceinline__ void gemv_heads(const Ring& ring, const Cons& cs, int
     constexpr int VEC = L::VEC, NCH = L::NCH, DPL = L::DPL;
     const int ntiles = (nunits + UPT - 1) / UPT;
     if (fill_n > 0) {  // uniform over the CTA
-        if (lane < ntiles) tile_ready_wait(ring, cs.gt + (uint32_t)lane);
+        if (ntiles > 0) tile_ready_wait_u(ring, cs.gt + (uint32_t)(ntiles - 1));
         __syncwarp();
         // (Once per generated sequence; the host enables this variant only for generations long enough to amortise it.
         // A software-pipelined version with two positions in flight per warp needed 64 more live registers and slowed
@@ -176,11 +199,11 @@ __device__ __forceinline__ void gemv_heads(const Ring& ring, const Cons& cs, int
                 }
             }
         }
-        bar_sync(1, MEGA_CONSUMERS);  // every warp read both tiles: nobody releases one before all are done
+        BAR1();  // every warp read both tiles: nobody releases one before all are done
     }
     const int t = warp >> 2;
     if (t >= ntiles) return;
-    if (lane == 0) tile_ready_wait(ring, cs.gt + (uint32_t)t);
+    tile_ready_wait_u(ring, cs.gt + (uint32_t)t);
     __syncwarp();
     if (warp < nunits) {
         const float* col = slot_ptr(ring, cs.gt + (uint32_t)t) + (warp & 3) * UF;
@@ -293,6 +316,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
             mbar_init(&ring.full[i], 1);
             mbar_init(&ring.empty[i], 4);  // the four reader warps of a tile
         }
+#ifdef GV_PROG
+        for (int q = 0; q < 8; ++q) bar_cnt()[q] = 0u;
+#endif
         ctl[0] = 0;
         ctl[1] = 0;
         ctl[2] = 0;
@@ -390,6 +416,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     // hop counter targets (counters are zero at launch): x1 / pp / x2 advance by a fixed amount per layer, so they are
     // derived from one layer counter; only the attention target (items vary with S) and the logits target are running sums
     unsigned lc = 0, t_ao = 0, t_lg = 0;
+    [[maybe_unused]] unsigned nbar = 0;  // GV_PROG: bar.sync instructions this thread executed
     float shift1 = 0.0f, shift2 = 0.0f;  // statistics shifts of ln_1 / ln_2: the means seen one layer earlier
 
     for (int i = 0; i < p.n_steps; ++i) {
@@ -427,6 +454,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                 const int ts = l * GV_TRACE_PER_LAYER;
                 // ---- QKV: [q|k|v] = LN1(x) . W_attn + b  (LN folded: GEMV on raw x, statistics in the epilogue) ----
                 {
+                    // this warp's c_attn units go to registers while the x2 hop of the previous block is in flight
+                    GemvRegs<NXV, GemvKU<NXV>::QKV> wq;
+#if GV_PRE_QKV
+                    gemv_preload(ring, cs, nun[PH_QKV], warp, lane, wq);
+                    cs.gt += (uint32_t)ntl[PH_QKV];
+#endif
                     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (l == 0) {
                         if (xvalid) {
@@ -445,23 +478,30 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     }
 #else
                     } else {
-                        hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, settle, hold_c, near);
-                        if (xvalid) ld_tagged_vec<4>(p.x2, 4 * tid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask, &x.x);
+                        hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, settle, hold_c, near); GV_NBAR(1);
+                        ld_tagged_vec_u<4>(p.x2, 4 * tid, xvalid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask, &x.x);
+                        if (!xvalid) x = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #endif
                     if (xvalid) *reinterpret_cast<float4*>(xres0 + 4 * tid) = x;
                     if (hold_c && tid == 0) *hold_c = 0;  // hop data is in registers: the producer may stream again
                     stamp(ts + 0);
+                    GV_MARK(1u);
                     stats_partial(x, xvalid, shift1, red, lane, warp);
-                    bar_sync(1, MEGA_CONSUMERS);
+                    BAR1(); GV_NBAR(1);
+                    GV_MARK(2u);
                     float mean, rstd;
                     stats_finish(red, inv_d, shift1, mean, rstd);
                     shift1 = mean;
                     stamp(ts + 1);
-                    gemv_dot<NXV, false>(ring, cs, nun[PH_QKV], xres0, warp, lane, [&](int u, float dot, float c2, float c1) {
+#if !GV_PRE_QKV
+                    gemv_preload(ring, cs, nun[PH_QKV], warp, lane, wq);
+                    cs.gt += (uint32_t)ntl[PH_QKV];
+#endif
+                    gemv_finish(nun[PH_QKV], xres0, warp, lane, wq, [&](int u, float dot, float c2, float c1) {
                         st_tagged(p.xq, ubeg[PH_QKV] + u, fmaf(rstd, fmaf(-mean, c1, dot), c2), tg + TG_XQ);
                     });
-                    cs.gt += (uint32_t)ntl[PH_QKV];
+                    GV_MARK(3u);
                     stamp(ts + 2);
                 }
                 if constexpr (PVW) {
@@ -508,15 +548,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                         }
                     }
                     // v of the position being decoded -> xo (the input of the per-head attn c_proj GEMV)
-                    hop_wait(hc + HC_XQ * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near);
+                    hop_wait(hc + HC_XQ * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near); GV_NBAR(1);
                     stamp(ts + 14);
-                    if (xvalid) {
+                    {
                         float4 v4;
-                        ld_tagged_vec<4>(p.xq, 2 * D + 4 * tid, tg + TG_XQ, tmask, &v4.x);
-                        *reinterpret_cast<float4*>(xo + 4 * tid) = v4;
+                        ld_tagged_vec_u<4>(p.xq, 2 * D + 4 * tid, xvalid, tg + TG_XQ, tmask, &v4.x);
+                        if (xvalid) *reinterpret_cast<float4*>(xo + 4 * tid) = v4;
                     }
                     if (hold_c && tid == 0) *hold_c = 0;
-                    bar_sync(1, MEGA_CONSUMERS);
+                    BAR1(); GV_NBAR(1);
                     stamp(ts + 15);
                     const int np = nun[PH_PROJ];
                     float* vw_new = vw_slice + (size_t)(S - 1) * H * 8;
@@ -561,20 +601,29 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                             const float* sb = p.sbuf + 2 * (size_t)(h0 + hh) * p.S_max;
                             const uint32_t tgs = tg + TG_AO;
                             float m = -INFINITY;
-                            for (int j4 = lane; j4 < S; j4 += 128) {
+                            for (int j0 = 0; j0 < S; j0 += 128) {  // uniform trip count: the warp polls as one
+                                const int j4 = j0 + lane;
                                 uint2 a[4];
-                                const bool pre = h0 == 0 && hh == warp && j4 == lane;  // requested before the GEMV
+                                const bool pre = h0 == 0 && hh == warp && j0 == 0;  // requested before the GEMV
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
+                                for (int k = 0; k < 4; ++k) {
+                                    a[k] = make_uint2(0u, tgs);
                                     if (j4 + 32 * k < S) a[k] = pre ? sa[k] : ld_x8(sb + 2 * (size_t)(j4 + 32 * k));
+                                }
+                                uint32_t spins = 0;
+                                for (;;) {
+                                    bool ok = true;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) ok = ok && ((a[k].y ^ tgs) & tmask) == 0u;
+                                    if (__all_sync(0xffffffffu, ok)) break;
+                                    GV_SPIN(spins, __LINE__, 0u, 0u);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        if (j4 + 32 * k < S && ((a[k].y ^ tgs) & tmask) != 0u) a[k] = ld_x8(sb + 2 * (size_t)(j4 + 32 * k));
+                                }
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     if (j4 + 32 * k < S) {
-                                        uint32_t spins = 0;
-                                        while (((a[k].y ^ tgs) & tmask) != 0u) {
-                                            if (++spins > MEGA_SPIN_LIMIT) __trap();
-                                            a[k] = ld_x8(sb + 2 * (size_t)(j4 + 32 * k));
-                                        }
                                         const float sv = __uint_as_float(a[k].x);
                                         ph[j4 + 32 * k] = sv;
                                         m = fmaxf(m, sv);
@@ -593,7 +642,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                             for (int jj = lane; jj < S; jj += 32) ph[jj] *= inv;
                         }
                         if (hold_c && tid == 0) *hold_c = 0;
-                        bar_sync(1, MEGA_CONSUMERS);
+                        BAR1(); GV_NBAR(1);
                         stamp(ts + 18);
                         // cached positions: (j, head) pairs dealt to the 32 thread groups; 8 consecutive threads read one
                         // 32-byte row segment of the slice.  The first eight pairs of every thread were requested from
@@ -617,13 +666,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                         }
                         if (g == 0)  // the position being decoded: its projected value is still in shared memory
                             for (int hh = 0; hh < nh; ++hh) acc = fmaf(psm[hh * S + S - 1], vwn[(h0 + hh) * 8 + colj], acc);
-                        bar_sync(1, MEGA_CONSUMERS);  // psm is rewritten by the next pass / redsm follows
+                        BAR1(); GV_NBAR(1);  // psm is rewritten by the next pass / redsm follows
                         stamp(ts + 19);
                     }
                     acc += __shfl_xor_sync(0xffffffffu, acc, 8);
                     acc += __shfl_xor_sync(0xffffffffu, acc, 16);
                     if (lane < 8) redsm[warp * 8 + lane] = acc;
-                    bar_sync(1, MEGA_CONSUMERS);
+                    BAR1(); GV_NBAR(1);
                     if (tid < np) {
                         float o = 0.0f;
 #pragma unroll
@@ -652,13 +701,23 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                         default: break;
                     }
 #undef GV_ATT_CASE
+                    GV_NBAR(2);
+                    GV_MARK(4u);
                     hop_arrive(hc + HC_AO * GV_HOP_STRIDE, tid);
                 }
                 t_ao += (unsigned)n_items;
                 stamp(ts + 3);
                 // ---- PROJ: merge attention partials -> o ; x1 = x + o . W_proj + b ----
                 {
-                    hop_wait(hc + HC_AO * GV_HOP_STRIDE, t_ao, tid, tmask, settle, hold_c, near_ao);
+                    // the attn c_proj unit of this warp goes to registers while the CTA waits for the attention items
+                    GemvRegs<NXV, GemvKU<NXV>::PROJ> wpj;
+#if GV_PRE_PROJ
+                    gemv_preload(ring, cs, nun[PH_PROJ], warp, lane, wpj);
+                    cs.gt += (uint32_t)ntl[PH_PROJ];
+#endif
+                    GV_MARK(5u);
+                    hop_wait(hc + HC_AO * GV_HOP_STRIDE, t_ao, tid, tmask, settle, hold_c, near_ao); GV_NBAR(1);
+                    GV_MARK(6u);
                     if (xvalid) {
                         const int h = (4 * tid) / HD, d = (4 * tid) % HD;
                         const uint32_t tga = tg + TG_AO;
@@ -679,8 +738,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                                 if (s0 + q < nsplit) {
                                     const int it = h * nsplit + s0 + q;
                                     uint32_t spins = 0;
-                                    while (!(tags_ok(a[q], tga, tmask) && tags_ok(b[q], tga, tmask) && tags_ok(c[q], tga, tmask))) {
-                                        if (++spins > MEGA_SPIN_LIMIT) __trap();
+                                    // the warp leaves the poll as one (xvalid is warp-uniform: D is a multiple of 128)
+                                    while (!__all_sync(0xffffffffu, tags_ok(a[q], tga, tmask) && tags_ok(b[q], tga, tmask) &&
+                                                                        tags_ok(c[q], tga, tmask))) {
+                                        GV_SPIN(spins, __LINE__, 0u, 0u);
                                         a[q] = ld_x16(p.att_ml + 2 * (size_t)(it * 2));
                                         b[q] = ld_x16(p.att_o + 2 * (size_t)(it * HD + d));
                                         c[q] = ld_x16(p.att_o + 2 * (size_t)(it * HD + d + 2));
@@ -702,12 +763,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     }
                     if (hold_c && tid == 0) *hold_c = 0;  // hop data is in registers: the producer may stream again
                     stamp(ts + 4);
-                    bar_sync(1, MEGA_CONSUMERS);
-                    gemv_dot<NXV, false>(ring, cs, nun[PH_PROJ], xo, warp, lane, [&](int u, float dot, float c2, float) {
+                    BAR1(); GV_NBAR(1);
+#if !GV_PRE_PROJ
+                    gemv_preload(ring, cs, nun[PH_PROJ], warp, lane, wpj);
+                    cs.gt += (uint32_t)ntl[PH_PROJ];
+#endif
+                    gemv_finish(nun[PH_PROJ], xo, warp, lane, wpj, [&](int u, float dot, float c2, float) {
                         const int col = ubeg[PH_PROJ] + u;
                         st_tagged(p.x1, col, xres0[col] + (dot + c2), tg + TG_X1);
                     });
-                    cs.gt += (uint32_t)ntl[PH_PROJ];
                     stamp(ts + 5);
                     stamp_wait(ts + 12);
                     hop_arrive(hc + HC_X1 * GV_HOP_STRIDE, tid);
@@ -715,29 +779,30 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                 }
                 // ---- FC + P2: u = gelu_new(LN2(x1) . W_fc + b) (kept in this CTA) -> partial of u . W_proj2 ----
                 {
-                    hop_wait(hc + HC_X1 * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near);
+                    // the c_fc units of this warp go to registers while the x1 hop is in flight (the weights do not depend on it)
+                    GemvRegs<NXV, GemvKU<NXV>::FC> wfc;
+                    gemv_preload(ring, cs, nun[PH_FC], warp, lane, wfc);
+                    cs.gt += (uint32_t)ntl[PH_FC];
+                    hop_wait(hc + HC_X1 * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near); GV_NBAR(1);
                     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (xvalid) {
-                        ld_tagged_vec<4>(p.x1, 4 * tid, tg + TG_X1, tmask, &x.x);
-                        *reinterpret_cast<float4*>(xres1 + 4 * tid) = x;
-                    }
+                    ld_tagged_vec_u<4>(p.x1, 4 * tid, xvalid, tg + TG_X1, tmask, &x.x);
+                    if (xvalid) *reinterpret_cast<float4*>(xres1 + 4 * tid) = x;
                     if (hold_c && tid == 0) *hold_c = 0;  // hop data is in registers: the producer may stream again
                     stamp(ts + 6);
                     stats_partial(x, xvalid, shift2, red + 16, lane, warp);
-                    bar_sync(1, MEGA_CONSUMERS);
+                    BAR1(); GV_NBAR(1);
                     float mean, rstd;
                     stats_finish(red + 16, inv_d, shift2, mean, rstd);
                     shift2 = mean;
                     stamp(ts + 7);
-                    gemv_dot<NXV, true>(ring, cs, nun[PH_FC], xres1, warp, lane, [&](int u, float dot, float c2, float c1) {
+                    gemv_finish(nun[PH_FC], xres1, warp, lane, wfc, [&](int u, float dot, float c2, float c1) {
                         us[u] = gelu_new(fmaf(rstd, fmaf(-mean, c1, dot), c2));
                     });
-                    cs.gt += (uint32_t)ntl[PH_FC];
-                    bar_sync(1, MEGA_CONSUMERS);
+                    BAR1(); GV_NBAR(1);
                     stamp(ts + 8);
                     gemv_outer<NXV>(ring, cs, nun[PH_P2], us, tid, lane, warp, part);
                     cs.gt += (uint32_t)ntl[PH_P2];
-                    bar_sync(1, MEGA_CONSUMERS);
+                    BAR1(); GV_NBAR(1);
 #if GV_ATOMIC_RED
                     unsigned long long* accl = p.acc + ((size_t)((fwd - 1u) & 1u) * p.L + l) * D + 4 * tid;
                     float4 b2 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -754,14 +819,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     stamp_wait(ts + 13);
                     hop_arrive(hc + HC_PP * GV_HOP_STRIDE, tid);
                     // x2 = x1 + b + sum of the G partials: every CTA reads the finished accumulators itself
-                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near);
+                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near); GV_NBAR(1);
                     if (xvalid) {
                         const unsigned long long full_count = (unsigned long long)(G & 0xff);
                         ulonglong2 w0 = ld_x2u64(accl), w1 = ld_x2u64(accl + 2);
                         uint32_t spins = 0;
                         while (tmask != 0u && (((w0.x & 0xffull) != full_count) || ((w0.y & 0xffull) != full_count) ||
                                                ((w1.x & 0xffull) != full_count) || ((w1.y & 0xffull) != full_count))) {
-                            if (++spins > MEGA_SPIN_LIMIT) __trap();
+                            GV_SPIN(spins, __LINE__, 0u, 0u);
                             w0 = ld_x2u64(accl);
                             w1 = ld_x2u64(accl + 2);
                         }
@@ -784,7 +849,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
 #if GV_PP_COUNTER
                     hop_arrive(hc + HC_PP * GV_HOP_STRIDE, tid);
 #else
-                    bar_sync(1, MEGA_CONSUMERS);  // `part` / `gat` alias: all reads of `part` precede the gather below
+                    BAR1(); GV_NBAR(1);  // `part` / `gat` alias: all reads of `part` precede the gather below
 #endif
                 }
                 // ---- RED: x2 = x1 + b + sum over CTAs of the partials (8 outputs per reducer CTA) ----
@@ -792,7 +857,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     float b2 = 0.0f;
                     if (lane == 0) b2 = __ldg(p.blob + p.proj2_b_off + (long long)l * p.layer_stride + cta * 8 + warp);
 #if GV_PP_COUNTER
-                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near);
+                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near); GV_NBAR(1);
 #endif
                     stamp(ts + 10);
                     {   // load q: 16 bytes {v, tag, v, tag} of source CTA q / 4, outputs 2 (q % 4), +1; three rounds in flight
@@ -808,8 +873,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                             if (q < nq) a[rr] = ld_x16(ap[rr]);
                         }
                         uint32_t spins = 0;
-                        while (!(tags_ok(a[0], tgp, tmask) && tags_ok(a[1], tgp, tmask) && tags_ok(a[2], tgp, tmask))) {
-                            if (++spins > MEGA_SPIN_LIMIT) __trap();
+                        while (!__all_sync(0xffffffffu, tags_ok(a[0], tgp, tmask) && tags_ok(a[1], tgp, tmask) && tags_ok(a[2], tgp, tmask))) {
+                            GV_SPIN(spins, __LINE__, 0u, 0u);
 #pragma unroll
                             for (int rr = 0; rr < 3; ++rr)
                                 if (tid + rr * MEGA_CONSUMERS < nq) a[rr] = ld_x16(ap[rr]);
@@ -823,7 +888,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                         }
                     }
                     if (hold_c && tid == 0) *hold_c = 0;  // hop data is in registers: the producer may stream again
-                    bar_sync(1, MEGA_CONSUMERS);
+                    BAR1(); GV_NBAR(1);
                     {
                         float s = 0.0f;
                         for (int c = lane; c < G; c += 32) s += gat[c * 8 + warp];
@@ -843,37 +908,54 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
             {
                 const uint32_t tg = tbase + (uint32_t)GV_TAGS_PER_LAYER * (uint32_t)p.L;
                 const int ts = p.L * GV_TRACE_PER_LAYER;
+                // the logits-head units (they follow the LayerNorm-parameter tile in the stream) go to registers before the hop
+                GemvRegs<NXV, GemvKU<NXV>::HEAD> wh;
+#if GV_PRE_HEAD
+                gemv_preload(ring, Cons{cs.gt + 1u, cs.wacc}, nun[PH_HEAD], warp, lane, wh);
+#endif
 #if GV_ATOMIC_RED
                 lat = xnext;
 #else
-                hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, settle, hold_c, near);
-                if (xvalid) ld_tagged_vec<4>(p.x2, 4 * tid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask, &lat.x);
+                hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, settle, hold_c, near); GV_NBAR(1);
+                ld_tagged_vec_u<4>(p.x2, 4 * tid, xvalid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask, &lat.x);
+                if (!xvalid) lat = make_float4(0.f, 0.f, 0.f, 0.f);
 #endif
                 if (hold_c && tid == 0) *hold_c = 0;
                 stamp(ts + 0);
                 const float* lnp = tile_wait(ring, cs, cs.gt, lane);  // all warps read the parameter tile
                 ln_quad(lat, xvalid, D, lnp, lnp + D, red, tid);
-                bar_sync(1, MEGA_CONSUMERS);  // `red` is reused by the second LayerNorm
+                BAR1(); GV_NBAR(1);  // `red` is reused by the second LayerNorm
                 ln_quad(lat, xvalid, D, lnp + 2 * D, lnp + 3 * D, red, tid);
                 if (xvalid) *reinterpret_cast<float4*>(xo + 4 * tid) = lat;
-                bar_sync(1, MEGA_CONSUMERS);
+                BAR1(); GV_NBAR(1);
                 if (warp == 0) tile_release(ring, cs.gt, lane, 4u);
                 cs.gt += 1u;
-                gemv_dot<NXV, false>(ring, cs, nun[PH_HEAD], xo, warp, lane,
-                              [&](int u, float dot, float c2, float) { st_tagged(p.lg, ubeg[PH_HEAD] + u, dot + c2, tg); });
+#if !GV_PRE_HEAD
+                gemv_preload(ring, Cons{cs.gt, cs.wacc}, nun[PH_HEAD], warp, lane, wh);
+#endif
+                gemv_finish(nun[PH_HEAD], xo, warp, lane, wh,
+                                 [&](int u, float dot, float c2, float) { st_tagged(p.lg, ubeg[PH_HEAD] + u, dot + c2, tg); });
                 cs.gt += (uint32_t)ntl[PH_HEAD];
                 stamp(ts + 1);
                 hop_arrive(hc + HC_LG * GV_HOP_STRIDE, tid);
                 t_lg += (unsigned)G;
-                hop_wait(hc + HC_LG * GV_HOP_STRIDE, t_lg, tid, tmask, settle, hold_c, near);
-                for (int e = 2 * tid; e < p.V; e += 2 * MEGA_CONSUMERS) {
-                    if (e + 1 < p.V) {
-                        const float2 v = ld_tagged2(p.lg, e, tg, tmask);
-                        slog[e] = v.x;
-                        slog[e + 1] = v.y;
-                    } else {
-                        slog[e] = ld_tagged1(p.lg, e, tg, tmask);
+                hop_wait(hc + HC_LG * GV_HOP_STRIDE, t_lg, tid, tmask, settle, hold_c, near); GV_NBAR(1);
+                for (int e0 = 0; e0 < p.Vpad; e0 += 2 * MEGA_CONSUMERS) {  // uniform trip count; lg holds Vpad (even) tagged words
+                    const int e = e0 + 2 * tid;
+                    const bool v0 = e < p.V, v1 = e + 1 < p.V;
+                    uint4 a = make_uint4(0u, tg, 0u, tg);
+                    uint32_t spins = 0;
+                    for (;;) {  // the warp leaves the poll as one (see ld_tagged_vec_u)
+                        bool ok = true;
+                        if (v0) {
+                            a = ld_x16(p.lg + 2 * (size_t)e);
+                            ok = ((a.y ^ tg) & tmask) == 0u && (!v1 || ((a.w ^ tg) & tmask) == 0u);
+                        }
+                        if (__all_sync(0xffffffffu, ok)) break;
+                        GV_SPIN(spins, __LINE__, (unsigned)e, tg - a.y);
                     }
+                    if (v0) slog[e] = __uint_as_float(a.x);
+                    if (v1) slog[e + 1] = __uint_as_float(a.z);
                 }
                 if (hold_c && tid == 0) *hold_c = 0;
                 stamp(ts + 2);
@@ -883,10 +965,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
             for (int e = tid; e < p.V; e += MEGA_CONSUMERS) slog[e] = ldcg(p.pend_logits + e);
             if (xvalid) lat = ldcg4(p.pend_latent + 4 * tid);
         }
-        bar_sync(1, MEGA_CONSUMERS);  // slog complete; attention / gather scratch (aliasing `keys`) is dead
+        BAR1(); GV_NBAR(1);  // slog complete; attention / gather scratch (aliasing `keys`) is dead
         // ------------- sample + emit (every CTA computes the same token) -------------
         int tok = sample_token([&](int e) { return slog[e]; }, seen, scfg, p.noise ? p.noise + (size_t)i * p.V : nullptr, p.seed,
-                               (uint32_t)n, 0u, keys, fscr, iscr, tid, [] { bar_sync(1, MEGA_CONSUMERS); });
+                               (uint32_t)n, 0u, keys, fscr, iscr, tid, [] { BAR1(); });
         stamp(p.L * GV_TRACE_PER_LAYER + 3);
         if (p.forced) {
             const long long f = p.forced[i];
@@ -905,7 +987,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
         if (!p.ignore_eos && tok == p.stop_token) finished = 1;
         n += 1;
         emitted += 1;
-        bar_sync(1, MEGA_CONSUMERS);  // seen[] update visible to the next step's sampler; slog / keys free
+        BAR1(); GV_NBAR(1);  // seen[] update visible to the next step's sampler; slog / keys free
         if (finished || n >= p.max_total) {
             done = 1;
             break;
@@ -918,7 +1000,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
         ctl[0] = 1;
     }
     if (cta == 0) {
-        bar_sync(1, MEGA_CONSUMERS);
+        BAR1(); GV_NBAR(1);
         for (int q = tid; q < p.Vpad; q += MEGA_CONSUMERS) p.seen_out[q] = seen[q];
         if (tid == 0) {
             GenState* so = p.st_out;
@@ -971,6 +1053,7 @@ cudaError_t launch_decode_mega(const MegaParams& p, int grid, cudaStream_t st) {
     const int hd = p.D / p.H;
     if (p.D % 128 || p.D > 1024 || !(hd == 32 || hd == 64 || hd == 128 || hd == 256)) return cudaErrorInvalidValue;
     if ((size_t)grid * 8 * sizeof(float) > 9728 || p.H * 8 > grid) return cudaErrorInvalidValue;
+    if (grid < 128 || (p.V + grid - 1) / grid > 16) return cudaErrorInvalidValue;  // GemvKU: register sets per warp and phase
     const size_t smem = mega_smem_bytes(p.D, p.Vpad);
     switch (p.D / 128) {
         case 1: return launch_nxv<1>(p, grid, smem, st);
@@ -982,3 +1065,17 @@ cudaError_t launch_decode_mega(const MegaParams& p, int grid, cudaStream_t st) {
 }
 
 }  // namespace gv
+
+#ifdef GV_PROG
+extern "C" int genvc_debug_prog_copy(unsigned* pinned_host, void* stream) {
+    cudaMemcpyFromSymbolAsync(pinned_host + 160 * 8 * 4 + 160 * 256, gv::mega1::g_slip, sizeof(unsigned) * (8 + 8 * 64), 0, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    cudaMemcpyFromSymbolAsync(pinned_host + 160 * 8 * 4, gv::g_progt, sizeof(unsigned) * 160 * 256, 0, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    return (int)cudaMemcpyFromSymbolAsync(pinned_host, gv::g_prog, sizeof(unsigned) * 160 * 8 * 4, 0, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+}
+#endif
+#if GV_WAIT_DIAG
+// debug builds only (tools/wait_diag.py): binds the pinned host buffer the wait records of the single-row kernel go to
+extern "C" int genvc_debug_wait_bind(unsigned* pinned_host) {
+    return (int)cudaMemcpyToSymbol(gv::mega1::g_wait_buf, &pinned_host, sizeof(pinned_host));
+}
+#endif

@@ -24,6 +24,61 @@ namespace GV_MEGA_NS {
 #define MEGA_THREADS (MEGA_CONSUMERS + 128)  // + one producer warpgroup (one working thread): register reallocation is per warpgroup
 #define MEGA_SPIN_LIMIT (1u << 26)
 #define NSLOT GV_RING_NSLOT
+// Bounded waits.  Production: a wait that exceeds the spin limit faults the kernel (a pipeline bug must not hang the box).
+// Debug builds (tools/build_diag.sh, tools/wait_diag.py) record {line, cta, thread, a, b, late} of the waits that time out
+// in a pinned HOST buffer bound with genvc_debug_wait_bind() (host memory survives a faulted context):
+//   -DGV_WAIT_DIAG=1  short spin limit; the first timeout raises a flag that every other wait polls: each spinning thread records
+//                     where it stands exactly once, lingers, and the kernel faults: a deadlock becomes a list of who waited
+//                     for what;
+//   -DGV_WAIT_DIAG=2  production code in the spin loops (no flag polling): the waits that time out (2^22 spins) record, the first
+//                     one lingers 5 s so that every other stuck wait reaches its own limit and records too.
+#ifndef GV_WAIT_DIAG
+#define GV_WAIT_DIAG 0
+#endif
+#if GV_WAIT_DIAG
+#define GV_DIAG_RECORDS 65536
+__device__ unsigned* g_wait_buf;  // [8 + 8 * GV_DIAG_RECORDS] words of pinned host memory: [0] abort flag, [1] record count
+#if GV_WAIT_DIAG == 2
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void wait_diag_record(unsigned line, unsigned a, unsigned b, unsigned late) {
+    unsigned* buf = g_wait_buf;
+    if (buf == nullptr) return;
+    const unsigned k = atomicAdd_system(&buf[1], 1u);
+    if (k < GV_DIAG_RECORDS) {
+        volatile unsigned* r = buf + 8 + 8 * k;
+        r[0] = line; r[1] = blockIdx.x; r[2] = threadIdx.x; r[3] = a; r[4] = b; r[5] = late;
+    }
+    __threadfence_system();
+    atomicExch_system(&buf[0], 1u);
+}
+// record where this thread stands, linger so that every other stuck (or flag-polling) thread can record too, then fault
+#if GV_WAIT_DIAG == 2
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void wait_fault(unsigned line, unsigned a, unsigned b, unsigned late) {
+    wait_diag_record(line, a, b, late);
+    for (int k = 0; k < (GV_WAIT_DIAG == 2 ? 5000000 : 200000); ++k) __nanosleep(1000);
+    __trap();
+}
+#if GV_WAIT_DIAG == 1
+__device__ __forceinline__ void wait_check(uint32_t& spins, unsigned line, unsigned a, unsigned b) {
+    if (((++spins) & 0x3ffu) == 0u) {
+        const bool flag = g_wait_buf != nullptr && *(volatile unsigned*)g_wait_buf != 0u;
+        if (flag || spins > (1u << 21)) wait_fault(line, a, b, flag ? 1u : 0u);
+    }
+}
+#define GV_SPIN(spins, line, a, b) wait_check(spins, line, a, b)
+#else
+#define GV_SPIN(spins, line, a, b) if (++spins > (1u << 22)) wait_fault(line, a, b, 0u)
+#endif
+#else
+#define GV_SPIN(spins, line, a, b) if (++spins > MEGA_SPIN_LIMIT) __trap()
+#endif
 #define UPT GV_MEGA_UPT
 // scratch region (never live together): attention per-warp (max, sum) + PV partials (1 KB + 8 * hd floats <= 9 KB) |
 // mlp.c_proj group partials [2][D] floats | partial-sum gather [G][8] floats | sampling sort keys [GV_SORT_N] u64 = 16 KB.
@@ -66,10 +121,38 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 // Tile `idx` is ready: either the producer already saw its full barrier complete (one shared-memory load,
 // the common case: tiles are requested microseconds ahead) or this thread waits on the barrier itself
 // (mbarrier.try_wait costs several hundred cycles even when the phase is long complete).
+// The parity test is only meaningful once the slot's PREVIOUS occupant (tile idx - NSLOT) has landed: a barrier that is still
+// two phases behind answers "complete" for the parity of tile idx (phase aliasing).  A warp can be that far ahead of the
+// producer since the weight loads of a phase are hoisted above the hop before it (gemv_preload): three phases' worth of
+// tiles can be waited on before the other warp group's tiles of the first one have landed.  The producer's `landed`
+// counter (monotonic) closes the gap.
 __device__ __forceinline__ void tile_ready_wait(const Ring& r, uint32_t idx) {
-    if (ld_acquire_cta_shared(r.landed) > idx) return;
-    mbar_wait(&r.full[idx % NSLOT], (idx / NSLOT) & 1u);
+    uint32_t l = ld_acquire_cta_shared(r.landed);
+    if (l > idx) return;
+    uint32_t spins = 0;
+    while (l + NSLOT <= idx) {
+        GV_SPIN(spins, __LINE__, idx, l);
+        l = ld_acquire_cta_shared(r.landed);
+    }
+    spins = 0;
+    while (!mbar_try_wait(&r.full[idx % NSLOT], (idx / NSLOT) & 1u)) GV_SPIN(spins, __LINE__, idx, ld_acquire_cta_shared(r.landed));
 }
+
+// Warp-uniform wait (GV_UNIFORM_TILE_WAIT, single-row kernel): EVERY lane polls the producer's `landed` counter (one
+// broadcast shared-memory load per round) until tile `last_idx` -- and with it every earlier tile -- is in; the loop exit
+// is the same for all lanes, so the warp never splits on a weight wait.  (Lane-divergent mbarrier polling ahead of a block
+// barrier was the other ingredient of the barrier-slip deadlock described at ld_tagged_vec_u.)
+__device__ __forceinline__ void tile_ready_wait_u(const Ring& r, uint32_t last_idx) {
+    uint32_t spins = 0;
+    uint32_t l = ld_acquire_cta_shared(r.landed);
+    while (l <= last_idx) {
+        GV_SPIN(spins, __LINE__, last_idx, l);
+        l = ld_acquire_cta_shared(r.landed);
+    }
+}
+#ifndef GV_UNIFORM_TILE_WAIT
+#define GV_UNIFORM_TILE_WAIT 0
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // tagged exchange through L2: element i of a buffer lives at floats [2i, 2i+1] = {value, tag}
@@ -107,7 +190,7 @@ __device__ __forceinline__ float2 ld_tagged2(const float* buf, int idx, uint32_t
     uint4 a = ld_x16(p);
     uint32_t spins = 0;
     while (!tags_ok(a, tag, tmask)) {
-        if (++spins > MEGA_SPIN_LIMIT) __trap();
+        GV_SPIN(spins, __LINE__, (unsigned)idx, tag - a.y);
         a = ld_x16(p);
     }
     return make_float2(__uint_as_float(a.x), __uint_as_float(a.z));
@@ -117,7 +200,7 @@ __device__ __forceinline__ float ld_tagged1(const float* buf, int idx, uint32_t 
     uint2 a = ld_x8(p);
     uint32_t spins = 0;
     while (((a.y ^ tag) & tmask) != 0u) {
-        if (++spins > MEGA_SPIN_LIMIT) __trap();
+        GV_SPIN(spins, __LINE__, (unsigned)idx, tag - a.y);
         a = ld_x8(p);
     }
     return __uint_as_float(a.x);
@@ -137,12 +220,41 @@ __device__ __forceinline__ void ld_tagged_vec(const float* buf, int idx, uint32_
         uint4 a = ld_x16(p), b = ld_x16(p + 4);
         uint32_t spins = 0;
         while (!(tags_ok(a, tag, tmask) && tags_ok(b, tag, tmask))) {
-            if (++spins > MEGA_SPIN_LIMIT) __trap();
+            GV_SPIN(spins, __LINE__, (unsigned)idx, tag - a.y);
             a = ld_x16(p);
             b = ld_x16(p + 4);
         }
         out[0] = __uint_as_float(a.x);
         out[1] = __uint_as_float(a.z);
+        out[2] = __uint_as_float(b.x);
+        out[3] = __uint_as_float(b.z);
+    }
+}
+
+// Warp-uniform variants (single-row kernel): every lane of the warp calls them together (`valid` = this lane has an element)
+// and the warp leaves the poll loop as one -- lanes whose words are already there keep re-reading them until the slowest
+// lane's words arrive.  A per-lane exit leaves the warp split until the compiler's reconvergence point; on this toolchain a
+// block barrier further down was then seen releasing seven warps without the eighth (a warp counted twice), which deadlocks
+// the CTA.  The vote costs a few cycles per poll round; the extra polls hit lines that are complete.
+template <int NE>
+__device__ __forceinline__ void ld_tagged_vec_u(const float* buf, int idx, bool valid, uint32_t tag, uint32_t tmask, float* out) {
+    static_assert(NE == 2 || NE == 4, "NE must be 2 or 4");
+    const float* p = buf + 2 * (size_t)(valid ? idx : 0);
+    uint4 a = make_uint4(0u, tag, 0u, tag), b = a;
+    uint32_t spins = 0;
+    for (;;) {
+        bool ok = true;
+        if (valid) {
+            a = ld_x16(p);
+            if constexpr (NE == 4) b = ld_x16(p + 4);
+            ok = tags_ok(a, tag, tmask) && tags_ok(b, tag, tmask);
+        }
+        if (__all_sync(0xffffffffu, ok)) break;
+        GV_SPIN(spins, __LINE__, (unsigned)idx, tag - a.y);
+    }
+    out[0] = __uint_as_float(a.x);
+    out[1] = __uint_as_float(a.z);
+    if constexpr (NE == 4) {
         out[2] = __uint_as_float(b.x);
         out[3] = __uint_as_float(b.z);
     }
@@ -178,6 +290,42 @@ __device__ __forceinline__ float fix_value(unsigned long long w) {
     return (float)((double)((long long)w >> 8) * GV_FIX_INV);
 }
 
+// Block barrier of the consumer warps.  -DGV_PROG (debug): every warp counts its arrivals in shared memory and checks after
+// the barrier that all eight warps have arrived at least as often -- a barrier that releases without one of them (a warp
+// counted twice, e.g. arriving in two halves) is recorded with its source line in g_slip.
+#ifdef GV_PROG
+__device__ unsigned g_slip[8 + 8 * 64];
+__device__ __forceinline__ volatile unsigned* bar_cnt() {
+    __shared__ unsigned s_cnt[8];
+    return s_cnt;
+}
+__device__ __forceinline__ void bar_sync_chk(unsigned site) {
+    volatile unsigned* c = bar_cnt();
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    unsigned my = 0;
+    if (l == 0) {
+        my = c[w] + 1u;
+        c[w] = my;
+    }
+    bar_sync(1, MEGA_CONSUMERS);
+    if (l == 0) {
+        for (int q = 0; q < 8; ++q) {
+            const unsigned o = c[q];
+            if ((int)(o - my) < 0) {
+                const unsigned k = atomicAdd(&g_slip[0], 1u);
+                if (k < 64) {
+                    unsigned* r = g_slip + 8 + 8 * k;
+                    r[0] = site; r[1] = blockIdx.x; r[2] = (unsigned)w; r[3] = (unsigned)q; r[4] = my; r[5] = o;
+                }
+            }
+        }
+    }
+}
+#define BAR1() bar_sync_chk(__LINE__)
+#else
+#define BAR1() bar_sync(1, MEGA_CONSUMERS)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // hops: arrival counter (a hint: one poller per CTA) + block barrier
 // ---------------------------------------------------------------------------------------------
@@ -208,11 +356,11 @@ __device__ __forceinline__ void hop_wait(const unsigned* cnt, unsigned target, i
         if (hold) *hold = 1;  // the weight producer stops issuing bulk copies: they slow this SM's ordinary loads down
         uint32_t spins = 0;
         while (ld_relaxed_u32(cnt) + near < target) {
-            if (++spins > MEGA_SPIN_LIMIT) __trap();
+            GV_SPIN(spins, __LINE__, target, ld_relaxed_u32(cnt));
         }
         if (settle_ns) __nanosleep(settle_ns);
     }
-    bar_sync(1, MEGA_CONSUMERS);
+    BAR1();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -232,10 +380,14 @@ __device__ __forceinline__ const float* slot_ptr(const Ring& r, uint32_t idx) {
 __device__ __forceinline__ void group_wait(const Ring& r, const Cons& cs, int g, int ntiles, int lane) {
     long long t0 = 0;
     if (cs.wacc != nullptr && lane == 0) t0 = clock64();  // debug timeline
+#if GV_UNIFORM_TILE_WAIT
+    if (g < ntiles) tile_ready_wait_u(r, cs.gt + (uint32_t)(g + 2 * ((ntiles - 1 - g) / 2)));  // the group's last tile
+#else
     if (lane < 4) {
         const int t = g + 2 * lane;
         if (t < ntiles) tile_ready_wait(r, cs.gt + (uint32_t)t);
     }
+#endif
     __syncwarp();
     if (cs.wacc != nullptr && lane == 0) *cs.wacc += (unsigned long long)(clock64() - t0);
 }
@@ -249,6 +401,17 @@ __device__ __forceinline__ void group_release(const Ring& r, const Cons& cs, int
 }
 // single tile read by all warps (logits-head LayerNorm parameters)
 __device__ __forceinline__ const float* tile_wait(const Ring& r, const Cons& cs, uint32_t idx, int lane) {
+#if GV_UNIFORM_TILE_WAIT
+    if (cs.wacc != nullptr) {  // debug timeline
+        const long long t0 = clock64();
+        tile_ready_wait_u(r, idx);
+        if (lane == 0) *cs.wacc += (unsigned long long)(clock64() - t0);
+    } else {
+        tile_ready_wait_u(r, idx);
+    }
+    __syncwarp();
+    return slot_ptr(r, idx);
+#endif
     if (lane == 0) {
         if (cs.wacc != nullptr) {  // debug timeline
             const long long t0 = clock64();
@@ -311,13 +474,13 @@ __device__ __forceinline__ void ln_quad(float4& x, bool valid, int D, const floa
     float s = valid ? ((x.x + x.y) + (x.z + x.w)) : 0.0f;
     s = warp_sum(s);
     if (lane == 0) red[warp] = s;
-    bar_sync(1, MEGA_CONSUMERS);
+    BAR1();
     const float mean = sum8(red) / (float)D;
     const float d0 = x.x - mean, d1 = x.y - mean, d2 = x.z - mean, d3 = x.w - mean;
     float q = valid ? (fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3)) : 0.0f;
     q = warp_sum(q);
     if (lane == 0) red[8 + warp] = q;
-    bar_sync(1, MEGA_CONSUMERS);
+    BAR1();
     const float var = sum8(red + 8) / (float)D;
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
     if (valid) {
@@ -396,6 +559,84 @@ __device__ __forceinline__ void gemv_dot(const Ring& ring, const Cons& cs, int n
     const float2 c = up16 ? (up8 ? cc[3] : cc[2]) : (up8 ? cc[1] : cc[0]);
     if ((lane & 7) == 0 && u < nunits) epi(u, v, c.x, c.y);
 }
+
+// ---------------------------------------------------------------------------------------------
+// The same GEMV in two halves, so that the half that does not need the activations runs BEFORE the hop that delivers them:
+//   gemv_preload : wait for the phase's tiles, copy this warp's (up to four) units from the ring into registers
+//                  (4 x D / 32 weights per lane), release the tiles -- the producer refills them while the CTA waits
+//   gemv_finish  : activation vector -> registers, 32 FFMA per lane and unit, the transposing shuffle tree, epilogue
+// A phase then costs the FFMAs and the shuffle tree after its hop instead of the shared-memory round trips as well.
+// ---------------------------------------------------------------------------------------------
+// KU = units a warp can own in the phase (compile-time bound: units per CTA <= 8 KU), so that only that many register
+// sets exist: a phase with one unit per warp must not carry 128 registers across a function call.
+template <int NXV, int KU>
+struct GemvRegs {
+    float4 w[KU][NXV];
+    float2 cc[KU];
+};
+template <int NXV, int KU>
+__device__ __forceinline__ void gemv_preload(const Ring& ring, const Cons& cs, int nunits, int warp, int lane, GemvRegs<NXV, KU>& W) {
+    constexpr int D = NXV * 128, UF = D + 4;
+    const int ntiles = (nunits + UPT - 1) / UPT;
+    const int g = warp >> 2, r = warp & 3;
+    group_wait(ring, cs, g, ntiles, lane);
+#pragma unroll
+    for (int k = 0; k < KU; ++k) {
+        const int t = g + 2 * k;
+        W.cc[k] = make_float2(0.f, 0.f);
+        if (t * UPT + r < nunits) {
+            const float* col = slot_ptr(ring, cs.gt + (uint32_t)t) + r * UF;
+            W.cc[k] = *reinterpret_cast<const float2*>(col + D);
+#pragma unroll
+            for (int i = 0; i < NXV; ++i) W.w[k][i] = *reinterpret_cast<const float4*>(col + (i * 32 + lane) * 4);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NXV; ++i) W.w[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    group_release(ring, cs, g, ntiles, lane);
+}
+template <int NXV, int KU, class Epi>
+__device__ __forceinline__ void gemv_finish(int nunits, const float* xs, int warp, int lane, const GemvRegs<NXV, KU>& W, Epi epi) {
+    float4 xv[NXV];
+#pragma unroll
+    for (int i = 0; i < NXV; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + (i * 32 + lane) * 4);
+    float tot[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 cc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cc[k] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < KU; ++k) {
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NXV; ++i) {
+            a0 = fmaf(W.w[k][i].x, xv[i].x, a0);
+            a1 = fmaf(W.w[k][i].y, xv[i].y, a1);
+            a2 = fmaf(W.w[k][i].z, xv[i].z, a2);
+            a3 = fmaf(W.w[k][i].w, xv[i].w, a3);
+        }
+        tot[k] = (a0 + a1) + (a2 + a3);
+        cc[k] = W.cc[k];
+    }
+    const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+    const float k0 = up16 ? tot[2] : tot[0], s0 = up16 ? tot[0] : tot[2];
+    const float k1 = up16 ? tot[3] : tot[1], s1 = up16 ? tot[1] : tot[3];
+    const float h0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+    const float h1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+    const float keep = up8 ? h1 : h0, send = up8 ? h0 : h1;
+    float v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    const int q = lane >> 3;
+    const int u = warp + 8 * q;
+    const float2 c = up16 ? (up8 ? cc[3] : cc[2]) : (up8 ? cc[1] : cc[0]);
+    if ((lane & 7) == 0 && u < nunits) epi(u, v, c.x, c.y);
+}
+// register sets per warp and phase when the grid has at least 128 CTAs (launch_decode_mega checks): ceil(N / 128 / 8)
+template <int NXV> struct GemvKU {
+    static constexpr int QKV = (3 * NXV + 7) / 8, PROJ = (NXV + 7) / 8, FC = (4 * NXV + 7) / 8, HEAD = 2;
+};
 
 // mlp.c_proj split along K: unit k = row of W_proj2 owned by this CTA.  Warp group g takes tiles
 // t = g, g + 2, ...; thread j of the group (0..127) owns outputs [4j, 4j+4) and [D/2 + 4j, D/2 + 4j + 4) and
@@ -549,22 +790,26 @@ __device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict_
         bool ok = false;
         while (!ok) {
             ok = true;
+            [[maybe_unused]] unsigned seen_tag = tag_in;
             if (lane < EPW) {
                 const uint2 a = ld_x8(qp + 2 * (warp * EPW + lane));
                 ok = ((a.y ^ tag_in) & tmask) == 0u;
                 qmine = __uint_as_float(a.x);
+                seen_tag = a.y;
             }
+            [[maybe_unused]] unsigned bad = ok ? 0u : 1u;
             if (mine) {
                 const bool ok_k = ld_tagged_lane<VEC, NCH>(kp, lane, tag_in, tmask, knew);
                 const bool ok_v = ld_tagged_lane<VEC, NCH>(vp, lane, tag_in, tmask, vnew);
                 ok = ok && ok_k && ok_v;
+                bad |= (ok_k ? 0u : 2u) | (ok_v ? 0u : 4u);
             }
             ok = __all_sync(0xffffffffu, ok);
-            if (++spins > MEGA_SPIN_LIMIT) __trap();
+            GV_SPIN(spins, __LINE__, (unsigned)(h << 8) | bad, tag_in - seen_tag);
         }
         float* qs = wml + 16;
         if (lane < EPW) qs[warp * EPW + lane] = qmine;
-        bar_sync(1, MEGA_CONSUMERS);
+        BAR1();
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
 #pragma unroll
@@ -660,7 +905,7 @@ __device__ __noinline__ void att_item(float* __restrict__ Kc, float* __restrict_
         else if constexpr (VEC == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
         else *dst = o[0];
     }
-    bar_sync(1, MEGA_CONSUMERS);
+    BAR1();
     if constexpr (DBG) ck[5] = clock64();
     if (tid < HD) {
         float M = -INFINITY;
@@ -750,10 +995,10 @@ __device__ __noinline__ void score_item(float* __restrict__ Kc, float* __restric
                 ok = ok && ok_k && ok_v;
             }
             ok = __all_sync(0xffffffffu, ok);
-            if (++spins > MEGA_SPIN_LIMIT) __trap();
+            GV_SPIN(spins, __LINE__, 0u, 0u);
         }
         if (lane < EPW) qs[warp * EPW + lane] = qmine;
-        bar_sync(1, MEGA_CONSUMERS);
+        BAR1();
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
 #pragma unroll
@@ -835,7 +1080,7 @@ struct Producer {
         while (!mbar_test_wait(&ring.empty[slot], phase ^ 1u)) {
             advance();
             if (*stop) return false;
-            if (++spins > MEGA_SPIN_LIMIT) __trap();
+            GV_SPIN(spins, __LINE__, t, land);
         }
         if (*stop) return false;
         if (hold != nullptr) {
@@ -843,13 +1088,13 @@ struct Producer {
             while (*hold) {
                 advance();
                 if (*stop) return false;
-                if (++spins > MEGA_SPIN_LIMIT) __trap();
+                GV_SPIN(spins, __LINE__, 0u, 0u);
             }
         }
         spins = 0;
         while (t - land >= window) {  // at most `window` tiles requested but not landed
             advance();
-            if (++spins > MEGA_SPIN_LIMIT) __trap();
+            GV_SPIN(spins, __LINE__, 0u, 0u);
         }
         mbar_arrive_expect_tx(&ring.full[slot], floats * 4u);
         float* dst = ring.slots + (size_t)slot * ring.slot_floats;

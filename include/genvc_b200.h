@@ -200,6 +200,12 @@ uint64_t genvc_launch_count(const genvc_ctx* ctx);
  * switches it off. */
 int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, int step);
 
+/* Post-mortem aid (tools/hang_dump.py): byte offsets inside the workspace of the fused decode kernel's exchange buffers and
+ * arrival counters: out[0..11] = xq, att_o, att_ml, x1, pp, x2, lg, hops, sbuf offsets, then grid, counter stride (words),
+ * number of counters.  The buffers hold {value, tag} pairs; reading them from a side stream while a launch is stuck shows
+ * which producer of which exchange never stored. */
+int genvc_debug_layout(const genvc_ctx* ctx, uint64_t* out, int n);
+
 /* Tuning / debug knobs of the fused decode kernel (no reference counterpart):
  *   window > 0 : weight tiles the per-SM TMA producer keeps in flight (requested, not landed);
  *   nosync != 0: consumers do not wait for exchange data — results are garbage; probes the pure
