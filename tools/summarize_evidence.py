@@ -25,7 +25,7 @@ tag = sys.argv[1]
 src = os.path.join(ROOT, "gpurun_out", tag)
 dst = os.path.join(ROOT, "profiles", tag)
 os.makedirs(dst, exist_ok=True)
-for f in ("gpu.txt",):
+for f in ("gpu.txt", "bench.json", "bench_cfg3.json", "bench_cfg4.json", "timeline.txt", "batch_bench.json"):
     if os.path.exists(os.path.join(src, f)):
         shutil.copy(os.path.join(src, f), dst)
 
@@ -79,6 +79,7 @@ NOTES = {
     "attention": "causal attention of the prefill (48 rows x 4 heads x 256)",
     "splitk_ln": "split-K reduction + bias + residual + LayerNorm epilogue of the prefill GEMMs",
     "kv_attention": "single-query KV-cache attention (BASELINE configs[4] microbenchmark)",
+    "pc_attention_tc": "perceiver cross-attention on tcgen05 (one CTA per element and head)",
 }
 for rep in sorted(f for f in os.listdir(src) if f.endswith(".ncu-rep")):
     name = rep[:-8]
