@@ -335,8 +335,13 @@ def run_cfg2(args, rank: int, world: int, local_rank: int):
         return consume(g.get_generator(fake_inputs=fake, **kw))
 
     # ---- warm-up
+    toks = None
     for i in range(args.warmup):
-        segment(cond_dev, codes_dev[i])
+        toks, _ = segment(cond_dev, codes_dev[i])
+    if world > 1:
+        # the first all-gather builds NCCL's channels (tens of ms): part of the warm-up, not of a timed step
+        warm = torch.stack(toks, 1) if toks else torch.zeros((1, 1), dtype=torch.int64, device=dev)
+        gather_ids(warm, world, pad=g.stop_audio_token)
     # ---- timed: device-resident inputs, no per-launch instrumentation
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None

@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libgenvc_b200.so")
-SOURCES = ["api.cu", "ops.cu", "decode_mega.cu", "decode_batch.cu", "gemm_tc.cu"]
+SOURCES = ["api.cu", "ops.cu", "decode_mega.cu", "decode_batch.cu", "gemm_tc.cu", "vocoder.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -1,0 +1,329 @@
+// HiFi-GAN generator building blocks (the stage right after the codec-token path):
+//   reference  layers/hifigan.py:118-153 (ResBlock2), :28-116 (ResBlock1), :156-232 (HiFiGAN.forward)
+// Two stateless kernels behind the C ABI (include/genvc_b200.h: genvc_conv1d, genvc_conv_transpose1d); the host side
+// (genvc_b200/vocoder.py) strings them together exactly as HiFiGAN.forward does.  Everything that surrounds a convolution in
+// the reference is folded into it:
+//   * leaky_relu in front of the conv  -> applied while the input tile is staged in shared memory (pre_slope; 1 = none)
+//   * bias, the residual `xt + x`       -> epilogue
+//   * `xs += resblock(x)`, `xs / num_kernels` -> epilogue accumulates into y and scales (accumulate, out_scale)
+//   * tanh of conv_post                 -> epilogue
+// so a ResBlock2 is two launches and no elementwise kernel exists.  fp32 FFMA out of shared memory: the whole generator is
+// 4.5 GFLOP per second of audio (channels 256 -> 32), i.e. launch- and latency-bound, not a tensor-core problem at
+// streaming chunk sizes (32 frames): the tiles are sized so that even the last stage (32 channels, 24 000 samples per
+// second of audio) fills the 148 SMs.
+// Weights are repacked by the host to [Cin][K][Cout] (Cout contiguous): a warp reads the four output channels of a thread
+// as one broadcast LDS.128.
+#include "common.cuh"
+#include "../../include/genvc_b200.h"
+#include <algorithm>
+
+namespace gv {
+
+constexpr int VC_THREADS = 256;
+constexpr int VC_CO_T = 32;    // output channels per block (8 channel groups x 4)
+constexpr int VC_T_T = 128;    // output samples per block (32 sample groups x 4)
+constexpr int VC_CI_C = 16;    // input channels staged per round
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.0f ? v : v * slope; }
+
+// y[b, co, t] = epi( bias[co] + sum_ci sum_j w[ci][j][co] * lrelu(x[b, ci, t + j * dil - pad]) )
+__global__ void __launch_bounds__(VC_THREADS)
+conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+              const float* __restrict__ res, float* __restrict__ y, int Cin, int Cout, int T, int K, int dil, int pad,
+              float pre_slope, int accumulate, float out_scale, int act_tanh, int ksplit, float* __restrict__ scratch) {
+    extern __shared__ float sm[];
+    const int halo = (K - 1) * dil;
+    const int XW = VC_T_T + halo;             // staged samples per input channel
+    float* xin = sm;                          // [VC_CI_C][XW]
+    float* ws = sm + VC_CI_C * XW;            // [VC_CI_C][K][VC_CO_T]
+    const int tid = threadIdx.x;
+    const int cg = tid >> 5, tg = tid & 31;   // channel group (warp), sample group (lane)
+    // split over the input channels (small layers: too few output tiles to fill the GPU): slice ks of ksplit writes its
+    // partial sums to scratch[ks][b][co][t]; splitk_epilogue_kernel adds the slices in a fixed order
+    const int t0 = blockIdx.x * VC_T_T, co0 = blockIdx.y * VC_CO_T, b = blockIdx.z / ksplit, ks = blockIdx.z % ksplit;
+    const int per = ((Cin + ksplit - 1) / ksplit + VC_CI_C - 1) / VC_CI_C * VC_CI_C;
+    const int c_begin = ks * per, c_end = min(Cin, c_begin + per);
+    const float* xb = x + (size_t)b * Cin * T;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][q] = 0.0f;
+
+    // Software pipeline: the global loads of round r + 1 are issued into registers before round r is computed, and
+    // written to shared memory after it -- a block has few rounds' worth of parallelism (one block per SM at streaming
+    // sizes), so an exposed L2 / HBM latency per round would dominate the layer.
+    constexpr int XMAX = 16, WMAX = 24;  // staged elements per thread (host checks the bounds)
+    const int nx = VC_CI_C * XW, nw = VC_CI_C * K * VC_CO_T;
+    float xreg[XMAX], wreg[WMAX];
+    auto fetch = [&](int c0) {
+#pragma unroll
+        for (int r = 0; r < XMAX; ++r) {
+            const int e = tid + r * VC_THREADS;
+            float v = 0.0f;
+            if (e < nx) {
+                const int ci = e / XW, s = e - ci * XW;
+                const int t = t0 + s - pad;
+                if (c0 + ci < c_end && t >= 0 && t < T) v = lrelu(__ldg(xb + (size_t)(c0 + ci) * T + t), pre_slope);
+            }
+            xreg[r] = v;
+        }
+#pragma unroll
+        for (int r = 0; r < WMAX; ++r) {
+            const int e = tid + r * VC_THREADS;
+            float v = 0.0f;
+            if (e < nw) {
+                const int co = e % VC_CO_T, cj = e / VC_CO_T;  // cj = ci * K + j
+                const int ci = cj / K;
+                if (c0 + ci < c_end && co0 + co < Cout) v = __ldg(w + ((size_t)(c0 + ci) * K + (cj - ci * K)) * Cout + co0 + co);
+            }
+            wreg[r] = v;
+        }
+    };
+    auto commit = [&]() {
+#pragma unroll
+        for (int r = 0; r < XMAX; ++r) {
+            const int e = tid + r * VC_THREADS;
+            if (e < nx) xin[e] = xreg[r];
+        }
+#pragma unroll
+        for (int r = 0; r < WMAX; ++r) {
+            const int e = tid + r * VC_THREADS;
+            if (e < nw) ws[e] = wreg[r];
+        }
+    };
+    if (c_begin < c_end) fetch(c_begin);
+    for (int c0 = c_begin; c0 < c_end; c0 += VC_CI_C) {
+        commit();
+        __syncthreads();
+        if (c0 + VC_CI_C < c_end) fetch(c0 + VC_CI_C);
+#pragma unroll 2
+        for (int ci = 0; ci < VC_CI_C; ++ci) {
+            const float* xr = xin + ci * XW + tg * 4;
+            const float* wr = ws + ci * K * VC_CO_T + cg * 4;
+            for (int j = 0; j < K; ++j) {
+                const float4 wv = *reinterpret_cast<const float4*>(wr + j * VC_CO_T);
+                const float* xp = xr + j * dil;
+                const float x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
+                acc[0][0] = fmaf(wv.x, x0, acc[0][0]); acc[0][1] = fmaf(wv.x, x1, acc[0][1]);
+                acc[0][2] = fmaf(wv.x, x2, acc[0][2]); acc[0][3] = fmaf(wv.x, x3, acc[0][3]);
+                acc[1][0] = fmaf(wv.y, x0, acc[1][0]); acc[1][1] = fmaf(wv.y, x1, acc[1][1]);
+                acc[1][2] = fmaf(wv.y, x2, acc[1][2]); acc[1][3] = fmaf(wv.y, x3, acc[1][3]);
+                acc[2][0] = fmaf(wv.z, x0, acc[2][0]); acc[2][1] = fmaf(wv.z, x1, acc[2][1]);
+                acc[2][2] = fmaf(wv.z, x2, acc[2][2]); acc[2][3] = fmaf(wv.z, x3, acc[2][3]);
+                acc[3][0] = fmaf(wv.w, x0, acc[3][0]); acc[3][1] = fmaf(wv.w, x1, acc[3][1]);
+                acc[3][2] = fmaf(wv.w, x2, acc[3][2]); acc[3][3] = fmaf(wv.w, x3, acc[3][3]);
+            }
+        }
+        __syncthreads();
+    }
+    if (ksplit > 1) {
+        const int Bn = gridDim.z / ksplit;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int co = co0 + cg * 4 + i;
+            if (co >= Cout) continue;
+            float* prow = scratch + (((size_t)ks * Bn + b) * Cout + co) * T;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int t = t0 + tg * 4 + q;
+                if (t < T) prow[t] = acc[i][q];
+            }
+        }
+        return;
+    }
+    // epilogue: bias, residual, accumulate / scale, tanh
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + cg * 4 + i;
+        if (co >= Cout) continue;
+        const float bv = bias ? __ldg(bias + co) : 0.0f;
+        const size_t row = ((size_t)b * Cout + co) * T;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int t = t0 + tg * 4 + q;
+            if (t >= T) continue;
+            float v = acc[i][q] + bv;
+            if (res) v += res[row + t];
+            if (accumulate) v += y[row + t];
+            v *= out_scale;
+            if (act_tanh) v = tanhf(v);
+            y[row + t] = v;
+        }
+    }
+}
+
+// y[b, co, t] = bias[co] + sum_ci sum_{kk = (t + pad) % stride + m * stride < K} w[ci][kk][co] * lrelu(x[b, ci, (t + pad - kk) / stride])
+__global__ void __launch_bounds__(VC_THREADS)
+conv_transpose1d_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                        float* __restrict__ y, int Cin, int Cout, int Tin, int Tout, int K, int stride, int pad, float pre_slope,
+                        int ksplit, float* __restrict__ scratch) {
+    extern __shared__ float sm[];
+    const int tid = threadIdx.x;
+    const int cg = tid >> 5, tg = tid & 31;
+    const int t0 = blockIdx.x * VC_T_T, co0 = blockIdx.y * VC_CO_T, b = blockIdx.z / ksplit, ks = blockIdx.z % ksplit;
+    const int per = ((Cin + ksplit - 1) / ksplit + VC_CI_C - 1) / VC_CI_C * VC_CI_C;
+    const int c_begin = ks * per, c_end = min(Cin, c_begin + per);
+    // input samples that can reach outputs [t0, t0 + VC_T_T): s in [(t0 + pad - (K - 1)) / stride, (t0 + VC_T_T - 1 + pad) / stride]
+    const int s_lo = (t0 + pad - (K - 1)) >= 0 ? (t0 + pad - (K - 1)) / stride : -(((K - 1) - t0 - pad + stride - 1) / stride);
+    const int XW = (VC_T_T + K - 1) / stride + 2;
+    float* xin = sm;                      // [VC_CI_C][XW]
+    float* ws = sm + VC_CI_C * XW;        // [VC_CI_C][K][VC_CO_T]
+    const float* xb = x + (size_t)b * Cin * Tin;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][q] = 0.0f;
+    int kk0[4], sr0[4];  // first tap and its (staged) input index for each of the thread's four outputs
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int tp = t0 + tg * 4 + q + pad;
+        kk0[q] = tp % stride;
+        sr0[q] = tp / stride - s_lo;
+    }
+    for (int c0 = c_begin; c0 < c_end; c0 += VC_CI_C) {
+        for (int e = tid; e < VC_CI_C * XW; e += VC_THREADS) {
+            const int ci = e / XW, s = s_lo + (e - ci * XW);
+            float v = 0.0f;
+            if (c0 + ci < c_end && s >= 0 && s < Tin) v = lrelu(__ldg(xb + (size_t)(c0 + ci) * Tin + s), pre_slope);
+            xin[e] = v;
+        }
+        for (int e = tid; e < VC_CI_C * K * VC_CO_T; e += VC_THREADS) {
+            const int co = e % VC_CO_T, cj = e / VC_CO_T;
+            const int ci = cj / K;
+            float v = 0.0f;
+            if (c0 + ci < c_end && co0 + co < Cout) v = __ldg(w + ((size_t)(c0 + ci) * K + (cj - ci * K)) * Cout + co0 + co);
+            ws[e] = v;
+        }
+        __syncthreads();
+        for (int ci = 0; ci < VC_CI_C; ++ci) {
+            const float* xr = xin + ci * XW;
+            const float* wr = ws + ci * K * VC_CO_T + cg * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int s = sr0[q];
+                for (int kk = kk0[q]; kk < K; kk += stride, --s) {
+                    const float xv = xr[s];  // s >= 0 by construction of s_lo; inputs outside [0, Tin) were staged as zeros
+                    const float4 wv = *reinterpret_cast<const float4*>(wr + kk * VC_CO_T);
+                    acc[0][q] = fmaf(wv.x, xv, acc[0][q]);
+                    acc[1][q] = fmaf(wv.y, xv, acc[1][q]);
+                    acc[2][q] = fmaf(wv.z, xv, acc[2][q]);
+                    acc[3][q] = fmaf(wv.w, xv, acc[3][q]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (ksplit > 1) {
+        const int Bn = gridDim.z / ksplit;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int co = co0 + cg * 4 + i;
+            if (co >= Cout) continue;
+            float* prow = scratch + (((size_t)ks * Bn + b) * Cout + co) * Tout;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int t = t0 + tg * 4 + q;
+                if (t < Tout) prow[t] = acc[i][q];
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + cg * 4 + i;
+        if (co >= Cout) continue;
+        const float bv = bias ? __ldg(bias + co) : 0.0f;
+        const size_t row = ((size_t)b * Cout + co) * Tout;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int t = t0 + tg * 4 + q;
+            if (t < Tout) y[row + t] = acc[i][q] + bv;
+        }
+    }
+}
+
+// sum of the ksplit partial slices in slice order, then the same epilogue as the unsplit kernels
+__global__ void __launch_bounds__(256)
+splitk_conv_epilogue_kernel(const float* __restrict__ scratch, const float* __restrict__ bias, const float* __restrict__ res,
+                            float* __restrict__ y, int ksplit, int B, int Cout, int T, int accumulate, float out_scale, int act_tanh) {
+    const size_t n = (size_t)B * Cout * T;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        float v = 0.0f;
+        for (int ks = 0; ks < ksplit; ++ks) v += scratch[(size_t)ks * n + e];
+        const int co = (int)((e / T) % Cout);
+        if (bias) v += __ldg(bias + co);
+        if (res) v += res[e];
+        if (accumulate) v += y[e];
+        v *= out_scale;
+        if (act_tanh) v = tanhf(v);
+        y[e] = v;
+    }
+}
+
+// slices so that small layers still put ~2 blocks on every SM; each slice keeps at least one staging round
+static int pick_ksplit(int tiles, int Cin, size_t out_elems, size_t scratch_floats) {
+    if (scratch_floats == 0) return 1;
+    int ks = 1;
+    while (tiles * ks < 200 && ks * 2 * VC_CI_C <= Cin && (size_t)(ks * 2) * out_elems <= scratch_floats) ks *= 2;
+    return ks;
+}
+
+}  // namespace gv
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int genvc_conv1d(const float* x, const float* w, const float* bias, const float* residual, float* y, int B, int Cin,
+                            int Cout, int T, int K, int dilation, int padding, float pre_slope, int accumulate, float out_scale,
+                            int act_tanh, float* scratch, uint64_t scratch_floats, void* stream) {
+    if (!x || !w || !y || B <= 0 || Cin <= 0 || Cout <= 0 || T <= 0 || K <= 0 || K > 31 || dilation <= 0 || padding < 0)
+        return GENVC_E_INVALID;
+    if (2 * padding != (K - 1) * dilation) return GENVC_E_INVALID;  // "same" convolutions only (utils.py:174 get_padding)
+    // register staging of the kernel: 16 input and 24 weight elements per thread and round
+    if (gv::VC_CI_C * (gv::VC_T_T + (K - 1) * dilation) > 16 * gv::VC_THREADS || gv::VC_CI_C * K * gv::VC_CO_T > 24 * gv::VC_THREADS)
+        return GENVC_E_UNSUPPORTED;
+    const size_t smem = ((size_t)gv::VC_CI_C * (gv::VC_T_T + (K - 1) * dilation) + (size_t)gv::VC_CI_C * K * gv::VC_CO_T) * sizeof(float);
+    if (smem > 200 * 1024) return GENVC_E_INVALID;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(gv::conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return GENVC_E_CUDA;
+    dim3 grid((T + gv::VC_T_T - 1) / gv::VC_T_T, (Cout + gv::VC_CO_T - 1) / gv::VC_CO_T, B);
+    const size_t out_elems = (size_t)B * Cout * T;
+    const int ks = gv::pick_ksplit((int)(grid.x * grid.y * grid.z), Cin, out_elems, scratch ? (size_t)scratch_floats : 0);
+    grid.z = B * ks;
+    gv::conv1d_kernel<<<grid, gv::VC_THREADS, smem, (cudaStream_t)stream>>>(x, w, bias, residual, y, Cin, Cout, T, K, dilation, padding,
+                                                                             pre_slope, accumulate, out_scale, act_tanh, ks, scratch);
+    if (ks > 1) {
+        const int blocks = (int)std::min<size_t>((out_elems + 255) / 256, 1184);
+        gv::splitk_conv_epilogue_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scratch, bias, residual, y, ks, B, Cout, T, accumulate,
+                                                                                  out_scale, act_tanh);
+    }
+    return cudaGetLastError() == cudaSuccess ? GENVC_OK : GENVC_E_CUDA;
+}
+
+extern "C" int genvc_conv_transpose1d(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout, int Tin,
+                                      int K, int stride, int padding, float pre_slope, float* scratch, uint64_t scratch_floats,
+                                      void* stream) {
+    if (!x || !w || !y || B <= 0 || Cin <= 0 || Cout <= 0 || Tin <= 0 || K <= 0 || K > 64 || stride <= 0 || padding < 0)
+        return GENVC_E_INVALID;
+    const int Tout = (Tin - 1) * stride - 2 * padding + K;  // torch.nn.ConvTranspose1d, output_padding = 0, dilation = 1
+    if (Tout <= 0) return GENVC_E_INVALID;
+    const size_t smem = ((size_t)gv::VC_CI_C * ((gv::VC_T_T + K - 1) / stride + 2) + (size_t)gv::VC_CI_C * K * gv::VC_CO_T) * sizeof(float);
+    if (smem > 200 * 1024) return GENVC_E_INVALID;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(gv::conv_transpose1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return GENVC_E_CUDA;
+    dim3 grid((Tout + gv::VC_T_T - 1) / gv::VC_T_T, (Cout + gv::VC_CO_T - 1) / gv::VC_CO_T, B);
+    const size_t out_elems = (size_t)B * Cout * Tout;
+    const int ks = gv::pick_ksplit((int)(grid.x * grid.y * grid.z), Cin, out_elems, scratch ? (size_t)scratch_floats : 0);
+    grid.z = B * ks;
+    gv::conv_transpose1d_kernel<<<grid, gv::VC_THREADS, smem, (cudaStream_t)stream>>>(x, w, bias, y, Cin, Cout, Tin, Tout, K, stride,
+                                                                                       padding, pre_slope, ks, scratch);
+    if (ks > 1) {
+        const int blocks = (int)std::min<size_t>((out_elems + 255) / 256, 1184);
+        gv::splitk_conv_epilogue_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scratch, bias, nullptr, y, ks, B, Cout, Tout, 0, 1.0f, 0);
+    }
+    return cudaGetLastError() == cudaSuccess ? GENVC_OK : GENVC_E_CUDA;
+}

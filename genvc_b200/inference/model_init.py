@@ -9,7 +9,8 @@ keeps working without coqpit.
 
 Stages outside this path (ContentVec, content-DVAE, mel front-end, HiFi-GAN; SURVEY.md §2 #9-#11,
 #16) are *attachment points* on the returned model: assign the reference's own modules to
-``model.content_extractor``, ``model.content_dvae``, ``model.hifigan`` and
+``model.content_extractor``, ``model.content_dvae``, ``model.hifigan`` (built on the CUDA library automatically when the
+checkpoint holds ``hifigan.*`` weights: ``genvc_b200/vocoder.py``) and
 ``model.torch_mel_spectrogram_style_encoder`` to run the full pipeline.
 """
 from __future__ import annotations
@@ -146,4 +147,19 @@ def model_from_checkpoint(ckpt_states: dict, device, max_batch: int = 1, max_mel
     model.gpt.eval()
     model.gpt.to(device)
     model.gpt.init_gpt_for_inference()
+    attach_cuda_hifigan(model, ckpt_states.get("model") or {}, ckpt_states["config"])
     return model, config
+
+
+def attach_cuda_hifigan(model, state_dict: dict, raw_config) -> bool:
+    """If the checkpoint carries the generator's weights (``hifigan.*``, as saved by ``trainers/hifigan_trainer.py``), the
+    vocoder runs on the CUDA library too (``genvc_b200/vocoder.py``, built from ``config.vocoder_config`` like
+    ``trainers/hifigan_trainer.py:47-55``); otherwise ``model.hifigan`` stays an attachment point."""
+    sd = {k[len("hifigan."):]: v for k, v in state_dict.items() if k.startswith("hifigan.")}
+    if not any(k.startswith("conv_pre.") for k in sd) or torch.device(model.device).type != "cuda":
+        return False
+    from ..vocoder import HiFiGAN
+
+    vc = raw_config.get("vocoder_config", {}) if isinstance(raw_config, dict) else getattr(raw_config, "vocoder_config", {})
+    model.hifigan = HiFiGAN.from_config(vc or {}, device=model.device).load_state_dict(sd)
+    return True

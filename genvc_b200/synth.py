@@ -129,3 +129,53 @@ def state_dict_digest(sd: Dict[str, torch.Tensor], keys=None) -> str:
         step = max(1, flat.numel() // 4096)
         h.update(flat[::step].contiguous().numpy().tobytes())
     return h.hexdigest()[:16]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# HiFi-GAN generator (the stage after the path): synthetic weights under the reference's state-dict names
+# ------------------------------------------------------------------------------------------------------------------
+HIFIGAN_DEFAULTS = dict(input_feat_dim=1024, upsample_initial_channel=256, resblock_kernel_sizes=(3, 5, 7),
+                        resblock_dilation_sizes=((1, 2), (2, 6), (3, 12)), upsample_rates=(8, 8, 4),
+                        upsample_kernel_sizes=(16, 16, 8), resblock_type="2")  # configs/vocoder_configs.py:7-20
+
+
+def hifigan_conv_shapes(cfg: dict):
+    """(name, weight shape, transposed?) of every conv of layers/hifigan.py::HiFiGAN in construction order (:166-207)."""
+    c0 = cfg["upsample_initial_channel"]
+    out = [("conv_pre", (c0, cfg["input_feat_dim"], 7), False)]
+    for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
+        out.append((f"ups.{i}", (c0 // 2 ** i, c0 // 2 ** (i + 1), k), True))  # ConvTranspose1d weight: [in, out, k]
+    nk = len(cfg["resblock_kernel_sizes"])
+    ch = c0
+    for i in range(len(cfg["upsample_rates"])):
+        ch = c0 // 2 ** (i + 1)
+        for j, (k, d) in enumerate(zip(cfg["resblock_kernel_sizes"], cfg["resblock_dilation_sizes"])):
+            names = [f"convs.{m}" for m in range(len(d))] if cfg["resblock_type"] != "1" else \
+                [f"convs{a}.{m}" for m in range(len(d)) for a in (1, 2)]
+            for nm in names:
+                out.append((f"resblocks.{i * nk + j}.{nm}", (ch, ch, k), False))
+    out.append(("conv_post", (1, ch, 7), False))
+    return out
+
+
+def synth_hifigan_state(seed: int = 77, weight_norm: bool = True, **overrides) -> Dict[str, torch.Tensor]:
+    """Random generator weights, keys as ``HiFiGAN.state_dict()`` with (old-style) weight norm: ``<conv>.weight_g``
+    [out,1,1], ``<conv>.weight_v``, ``<conv>.bias``.  Scales keep the activations O(1) through the stack so that a
+    parity test sees every layer."""
+    cfg = dict(HIFIGAN_DEFAULTS, **overrides)
+    gen = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for name, shape, transposed in hifigan_conv_shapes(cfg):
+        fan_in = (shape[0] if transposed else shape[1]) * shape[2]
+        taps = shape[2] / (shape[2] // 2 if transposed else 1)  # a transposed conv with k = 2 * stride sees 2 taps per output
+        v = torch.randn(shape, generator=gen) * (1.3 / (fan_in / (taps if transposed else 1)) ** 0.5)
+        n_bias = shape[1] if transposed else shape[0]
+        bias = torch.randn(n_bias, generator=gen) * 0.05
+        if weight_norm:
+            norm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, 1, 1)
+            sd[name + ".weight_g"] = norm * (0.8 + 0.4 * torch.rand(norm.shape, generator=gen))
+            sd[name + ".weight_v"] = v
+        else:
+            sd[name + ".weight"] = v
+        sd[name + ".bias"] = bias
+    return sd

@@ -200,6 +200,29 @@ uint64_t genvc_launch_count(const genvc_ctx* ctx);
  * switches it off. */
 int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, int step);
 
+/* ---- the stage after the path: HiFi-GAN generator building blocks ----
+ * Stateless (no context); device pointers; fp32; layouts [B, C, T].  The host side (genvc_b200/vocoder.py) strings them
+ * together as layers/hifigan.py:210-225 does.  Weights are passed REPACKED to [Cin][K][Cout]
+ * (reference: Conv1d weight [Cout][Cin][K] -> permute(1,2,0); ConvTranspose1d weight [Cin][Cout][K] -> permute(0,2,1)),
+ * weight norm already folded (w = g * v / ||v||).
+ *
+ * genvc_conv1d: "same" convolution, stride 1 (2 * padding == (K - 1) * dilation):
+ *   v = bias[co] + sum_ci sum_j w[ci][j][co] * lrelu(x[b][ci][t + j*dilation - padding], pre_slope)   (pre_slope 1 = no activation)
+ *   v += residual[b][co][t] if residual;  v += y[b][co][t] if accumulate;  v *= out_scale;  v = tanh(v) if act_tanh;  y = v
+ *   — i.e. `xt = c(leaky_relu(x)); x = xt + x` of ResBlock2 (layers/hifigan.py:147-152) is ONE call, and
+ *   `xs += resblock(x)`, `x = xs / num_kernels` (:216-221) ride in the epilogue of each block's last conv.
+ * genvc_conv_transpose1d: torch.nn.ConvTranspose1d(Cin, Cout, K, stride, padding) on lrelu(x, pre_slope)
+ *   (layers/hifigan.py:213-214); Tout = (Tin - 1) * stride - 2 * padding + K.
+ * scratch_dev (optional, scratch_floats floats, caller-owned): layers with too few output tiles to fill the GPU are split
+ *   over their input channels into up to scratch_floats / (B*Cout*T) slices that are summed in a fixed order (results do
+ *   not depend on timing); NULL keeps every layer in one pass. */
+int genvc_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, const float* residual_dev, float* y_dev,
+                 int B, int Cin, int Cout, int T, int K, int dilation, int padding, float pre_slope, int accumulate,
+                 float out_scale, int act_tanh, float* scratch_dev, uint64_t scratch_floats, void* stream);
+int genvc_conv_transpose1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* y_dev, int B, int Cin,
+                           int Cout, int Tin, int K, int stride, int padding, float pre_slope, float* scratch_dev,
+                           uint64_t scratch_floats, void* stream);
+
 /* Post-mortem aid (tools/hang_dump.py): byte offsets inside the workspace of the fused decode kernel's exchange buffers and
  * arrival counters: out[0..11] = xq, att_o, att_ml, x1, pp, x2, lg, hops, sbuf offsets, then grid, counter stride (words),
  * number of counters.  The buffers hold {value, tag} pairs; reading them from a side stream while a launch is stuck shows

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""HiFi-GAN generator (csrc/vocoder.cu) on one GPU: ms per streaming chunk (8 tokens = 32 frames = 8192 samples) and per 1 s /
+6 s segment, achieved GFLOP/s, and the CPU oracle on the same input beside it.   python tools/vocoder_bench.py [--no-cpu]"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from genvc_b200.synth import HIFIGAN_DEFAULTS, hifigan_conv_shapes, synth_hifigan_state
+from genvc_b200.vocoder import HiFiGAN
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--no-cpu", action="store_true")
+ap.add_argument("--reps", type=int, default=50)
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+cfg = dict(HIFIGAN_DEFAULTS)
+sd = synth_hifigan_state(77)
+v = HiFiGAN.from_config({}, device=dev).load_state_dict(sd)
+
+
+def flops(T):
+    """2 * MACs of one forward over T input frames."""
+    total, t = 0, T
+    shapes = {n: s for n, s, _ in hifigan_conv_shapes(cfg)}
+    total += 2 * shapes["conv_pre"][0] * shapes["conv_pre"][1] * 7 * t
+    for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
+        cin, cout, _ = shapes[f"ups.{i}"]
+        t *= u
+        total += 2 * cin * cout * (k // u) * t
+        for n, s in shapes.items():
+            if n.startswith("resblocks.") and int(n.split(".")[1]) // 3 == i:
+                total += 2 * s[0] * s[1] * s[2] * t
+    total += 2 * shapes["conv_post"][1] * 7 * t
+    return total
+
+
+out = {}
+for label, T in (("chunk_8_tokens", 32), ("segment_1s", 94), ("segment_6s", 563)):
+    x = torch.randn(1, 1024, T, device=dev)
+    for _ in range(3):
+        v(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        v(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.reps
+    r = {"frames": T, "samples": T * 256, "ms": round(ms, 4), "gflops": round(flops(T) / ms / 1e6, 1),
+         "audio_s": round(T * 256 / 24000, 3), "rtf": round(ms / 1e3 / (T * 256 / 24000), 6)}
+    if not a.no_cpu and T <= 94:
+        from oracle.hifigan_oracle import hifigan_forward
+        arch = {k: cfg[k] for k in ("resblock_kernel_sizes", "resblock_dilation_sizes", "upsample_rates", "upsample_kernel_sizes", "resblock_type")}
+        xc = x.cpu()
+        hifigan_forward(sd, xc, **arch)
+        t0 = time.time()
+        for _ in range(3):
+            yc = hifigan_forward(sd, xc, **arch)
+        r["cpu_oracle_ms"] = round((time.time() - t0) / 3 * 1e3, 2)
+        r["max_err_vs_oracle"] = float((v(x).cpu() - yc).abs().max())
+    out[label] = r
+out["launches_per_forward"] = 1 + 3 + 18 + 1
+print(json.dumps(out))
