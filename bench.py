@@ -144,12 +144,25 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.proc = None
+        if os.environ.get("GENVC_BENCH_NOSMI") == "1":  # debug: rule the sampler in or out as a perturbation
+            self.first = ""
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+        # nvidia-smi spends its first few hundred ms initialising NVML (driver locks that delay kernel launches): wait
+        # for its first sample so that only the cheap periodic queries overlap the timed region
+        self.first = ""
+        if self.proc is not None:
+            try:
+                import select
+                if select.select([self.proc.stdout], [], [], 5.0)[0]:
+                    self.first = self.proc.stdout.readline()
+            except Exception:
+                pass
 
     def stop(self, t0: float, t1: float) -> dict:
         if self.proc is None:
@@ -162,7 +175,7 @@ class ClockSampler:
             self.proc.kill()
             out = ""
         rows = []
-        for line in out.splitlines():
+        for line in (self.first + out).splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
@@ -345,17 +358,30 @@ def run_cfg2(args, rank: int, world: int, local_rank: int):
     # ---- timed: device-resident inputs, no per-launch instrumentation
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.3 if sampler else 0.0)
+    # the GPU must not idle into the timed region (starting nvidia-smi takes a few hundred ms on rank 0 and an idle GPU
+    # drops its clocks): every rank runs two more untimed segments right before the barrier
+    eng.timing = None  # (before the last warm-up segments: they must take the same host path as the timed ones)
+    for i in range(min(2, args.warmup)):
+        segment(cond_dev, codes_dev[i])
     barrier()
-    eng.timing = None
     launches0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+    gc.collect()
+    gc.disable()  # a generation-2 collection inside a 100 ms timed region is a 5-10 ms host stall (stays off: the process
+    #               only runs the remaining timed loops and exits)
     w0 = time.time()
     e0.record(torch.cuda.current_stream(dev))
     all_ids = []
+    dbg = os.environ.get("GENVC_BENCH_DEBUG") == "1"
+    marks = [time.perf_counter()]
     for i in range(args.steps):
         toks, _ = segment(cond_dev, codes_dev[args.warmup + i])
         all_ids.append(torch.stack(toks, 1))
+        if dbg:
+            marks.append(time.perf_counter())
+    if dbg and rank == 0:
+        print("per-step ms:", [round(1e3 * (b - a), 2) for a, b in zip(marks, marks[1:])], file=sys.stderr)
     local_ids = torch.cat(all_ids, 0)  # [steps, new_tokens]
     gathered = gather_ids(local_ids, world, pad=g.stop_audio_token)  # NCCL all-gather of the ids (no-op at N = 1)
     e1.record(torch.cuda.current_stream(dev))
@@ -415,6 +441,28 @@ def run_cfg2(args, rank: int, world: int, local_rank: int):
             pass
     first_chunk_ms = statistics.median(lat_ms[2:])
 
+    # ---- first AUDIO (informational; the stage after the path): the same, but the 8 latents stay on the
+    # device, go through the x4 interpolation and the CUDA HiFi-GAN generator (synthetic weights of the reference's vocoder
+    # config) and the 8192-sample waveform chunk is what reaches the host (inference_utils.py:196-207)
+    from genvc_b200.inference.inference_utils import _vocode
+    from genvc_b200.synth import synth_hifigan_state
+    from genvc_b200.vocoder import HiFiGAN
+    model.hifigan = HiFiGAN.from_config({}, device=dev).load_state_dict(synth_hifigan_state(77))
+    aud_ms = []
+    for i in range(8):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        cond = model.get_gpt_cond_latents_from_mels([mel_dev])
+        fake = g.compute_embeddings(cond, codes_dev[i % n_seg])
+        gen = g.get_generator(fake_inputs=fake, **kw)
+        lats = [next(gen)[1] for _ in range(CHUNK)]
+        wav = _vocode(model, torch.cat(lats, dim=0)[None, :])
+        wav.cpu()
+        aud_ms.append(1e3 * (time.perf_counter() - t0))
+        for _ in gen:  # drain
+            pass
+    first_audio_ms = statistics.median(aud_ms[2:])
+
     # ---- prefill alone (compute_embeddings + prefill of 48 rows), CUDA events
     pf = []
     for i in range(6):
@@ -436,6 +484,7 @@ def run_cfg2(args, rank: int, world: int, local_rank: int):
         "e2e": {"value": round(total_tokens / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "first_chunk_ms": round(first_chunk_ms, 3),
+        "first_audio_ms": round(first_audio_ms, 3),
         "prefill_ms": round(prefill_ms, 4),
         "decode_ms_per_token": roof["decode_ms_per_forward"],
         "init_ms": round(max_over_ranks(init_ms, dev, world), 1),
@@ -518,10 +567,14 @@ def run_utterances(args, name: str, rank: int, world: int, local_rank: int):
         job(False)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.3 if sampler else 0.0)
+    if args.warmup > 0:
+        job(False)  # keeps the GPU busy while nvidia-smi starts on rank 0 (an idle GPU drops its clocks)
     barrier()
     launches0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+    gc.collect()
+    gc.disable()  # see run_cfg2
     w0 = time.time()
     e0.record(torch.cuda.current_stream(dev))
     for _ in range(args.steps):
