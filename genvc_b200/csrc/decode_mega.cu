@@ -137,14 +137,9 @@ __device__ __forceinline__ float ld_cg_early(const float* p) {
 #ifdef GV_PROG
 // debug: per-warp progress markers (tools/hang_dump.py reads them from a side stream while a launch is stuck)
 __device__ unsigned g_prog[160 * 8 * 4];
-#define GV_MARK(code) do { if ((threadIdx.x & 31) == 0) { unsigned* g_ = g_prog + (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4; g_[0] = (code); g_[1] = (unsigned)lc; if ((code) == 1u) g_[2] = nbar; g_[3] = nbar; } } while (0)
-#define GV_NBAR(k) (nbar += (k))
-__device__ unsigned g_progt[160 * 256];
-#define GV_MARKT(code) do { g_progt[blockIdx.x * 256 + threadIdx.x] = ((unsigned)lc << 8) | (code); } while (0)
+#define GV_MARK(code) do { if ((threadIdx.x & 31) == 0) { unsigned* g_ = g_prog + (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4; g_[0] = (code); g_[1] = (unsigned)lc; } } while (0)
 #else
 #define GV_MARK(code) do { } while (0)
-#define GV_MARKT(code) do { } while (0)
-#define GV_NBAR(k) do { } while (0)
 #endif
 template <int NXV, int HD, class Epi, class Bias>
 __device__ __forceinline__ void gemv_heads(const Ring& ring, const Cons& cs, int nunits, const float* xs, int warp, int lane, Epi epi,
@@ -416,7 +411,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
     // hop counter targets (counters are zero at launch): x1 / pp / x2 advance by a fixed amount per layer, so they are
     // derived from one layer counter; only the attention target (items vary with S) and the logits target are running sums
     unsigned lc = 0, t_ao = 0, t_lg = 0;
-    [[maybe_unused]] unsigned nbar = 0;  // GV_PROG: bar.sync instructions this thread executed
     float shift1 = 0.0f, shift2 = 0.0f;  // statistics shifts of ln_1 / ln_2: the means seen one layer earlier
 
     for (int i = 0; i < p.n_steps; ++i) {
@@ -478,7 +472,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     }
 #else
                     } else {
-                        hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, settle, hold_c, near); GV_NBAR(1);
+                        hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, settle, hold_c, near);
                         ld_tagged_vec_u<4>(p.x2, 4 * tid, xvalid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask, &x.x);
                         if (!xvalid) x = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
@@ -488,7 +482,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     stamp(ts + 0);
                     GV_MARK(1u);
                     stats_partial(x, xvalid, shift1, red, lane, warp);
-                    BAR1(); GV_NBAR(1);
+                    BAR1();
                     GV_MARK(2u);
                     float mean, rstd;
                     stats_finish(red, inv_d, shift1, mean, rstd);
@@ -548,7 +542,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                         }
                     }
                     // v of the position being decoded -> xo (the input of the per-head attn c_proj GEMV)
-                    hop_wait(hc + HC_XQ * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near); GV_NBAR(1);
+                    hop_wait(hc + HC_XQ * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near);
                     stamp(ts + 14);
                     {
                         float4 v4;
@@ -556,7 +550,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                         if (xvalid) *reinterpret_cast<float4*>(xo + 4 * tid) = v4;
                     }
                     if (hold_c && tid == 0) *hold_c = 0;
-                    BAR1(); GV_NBAR(1);
+                    BAR1();
                     stamp(ts + 15);
                     const int np = nun[PH_PROJ];
                     float* vw_new = vw_slice + (size_t)(S - 1) * H * 8;
@@ -642,7 +636,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                             for (int jj = lane; jj < S; jj += 32) ph[jj] *= inv;
                         }
                         if (hold_c && tid == 0) *hold_c = 0;
-                        BAR1(); GV_NBAR(1);
+                        BAR1();
                         stamp(ts + 18);
                         // cached positions: (j, head) pairs dealt to the 32 thread groups; 8 consecutive threads read one
                         // 32-byte row segment of the slice.  The first eight pairs of every thread were requested from
@@ -666,13 +660,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                         }
                         if (g == 0)  // the position being decoded: its projected value is still in shared memory
                             for (int hh = 0; hh < nh; ++hh) acc = fmaf(psm[hh * S + S - 1], vwn[(h0 + hh) * 8 + colj], acc);
-                        BAR1(); GV_NBAR(1);  // psm is rewritten by the next pass / redsm follows
+                        BAR1();  // psm is rewritten by the next pass / redsm follows
                         stamp(ts + 19);
                     }
                     acc += __shfl_xor_sync(0xffffffffu, acc, 8);
                     acc += __shfl_xor_sync(0xffffffffu, acc, 16);
                     if (lane < 8) redsm[warp * 8 + lane] = acc;
-                    BAR1(); GV_NBAR(1);
+                    BAR1();
                     if (tid < np) {
                         float o = 0.0f;
 #pragma unroll
@@ -701,7 +695,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                         default: break;
                     }
 #undef GV_ATT_CASE
-                    GV_NBAR(2);
                     GV_MARK(4u);
                     hop_arrive(hc + HC_AO * GV_HOP_STRIDE, tid);
                 }
@@ -716,7 +709,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     cs.gt += (uint32_t)ntl[PH_PROJ];
 #endif
                     GV_MARK(5u);
-                    hop_wait(hc + HC_AO * GV_HOP_STRIDE, t_ao, tid, tmask, settle, hold_c, near_ao); GV_NBAR(1);
+                    hop_wait(hc + HC_AO * GV_HOP_STRIDE, t_ao, tid, tmask, settle, hold_c, near_ao);
                     GV_MARK(6u);
                     if (xvalid) {
                         const int h = (4 * tid) / HD, d = (4 * tid) % HD;
@@ -763,7 +756,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     }
                     if (hold_c && tid == 0) *hold_c = 0;  // hop data is in registers: the producer may stream again
                     stamp(ts + 4);
-                    BAR1(); GV_NBAR(1);
+                    BAR1();
 #if !GV_PRE_PROJ
                     gemv_preload(ring, cs, nun[PH_PROJ], warp, lane, wpj);
                     cs.gt += (uint32_t)ntl[PH_PROJ];
@@ -783,14 +776,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     GemvRegs<NXV, GemvKU<NXV>::FC> wfc;
                     gemv_preload(ring, cs, nun[PH_FC], warp, lane, wfc);
                     cs.gt += (uint32_t)ntl[PH_FC];
-                    hop_wait(hc + HC_X1 * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near); GV_NBAR(1);
+                    hop_wait(hc + HC_X1 * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near);
                     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
                     ld_tagged_vec_u<4>(p.x1, 4 * tid, xvalid, tg + TG_X1, tmask, &x.x);
                     if (xvalid) *reinterpret_cast<float4*>(xres1 + 4 * tid) = x;
                     if (hold_c && tid == 0) *hold_c = 0;  // hop data is in registers: the producer may stream again
                     stamp(ts + 6);
                     stats_partial(x, xvalid, shift2, red + 16, lane, warp);
-                    BAR1(); GV_NBAR(1);
+                    BAR1();
                     float mean, rstd;
                     stats_finish(red + 16, inv_d, shift2, mean, rstd);
                     shift2 = mean;
@@ -798,11 +791,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     gemv_finish(nun[PH_FC], xres1, warp, lane, wfc, [&](int u, float dot, float c2, float c1) {
                         us[u] = gelu_new(fmaf(rstd, fmaf(-mean, c1, dot), c2));
                     });
-                    BAR1(); GV_NBAR(1);
+                    BAR1();
                     stamp(ts + 8);
                     gemv_outer<NXV>(ring, cs, nun[PH_P2], us, tid, lane, warp, part);
                     cs.gt += (uint32_t)ntl[PH_P2];
-                    BAR1(); GV_NBAR(1);
+                    BAR1();
 #if GV_ATOMIC_RED
                     unsigned long long* accl = p.acc + ((size_t)((fwd - 1u) & 1u) * p.L + l) * D + 4 * tid;
                     float4 b2 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -819,7 +812,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     stamp_wait(ts + 13);
                     hop_arrive(hc + HC_PP * GV_HOP_STRIDE, tid);
                     // x2 = x1 + b + sum of the G partials: every CTA reads the finished accumulators itself
-                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near); GV_NBAR(1);
+                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near);
                     if (xvalid) {
                         const unsigned long long full_count = (unsigned long long)(G & 0xff);
                         ulonglong2 w0 = ld_x2u64(accl), w1 = ld_x2u64(accl + 2);
@@ -849,7 +842,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
 #if GV_PP_COUNTER
                     hop_arrive(hc + HC_PP * GV_HOP_STRIDE, tid);
 #else
-                    BAR1(); GV_NBAR(1);  // `part` / `gat` alias: all reads of `part` precede the gather below
+                    BAR1();  // `part` / `gat` alias: all reads of `part` precede the gather below
 #endif
                 }
                 // ---- RED: x2 = x1 + b + sum over CTAs of the partials (8 outputs per reducer CTA) ----
@@ -857,7 +850,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                     float b2 = 0.0f;
                     if (lane == 0) b2 = __ldg(p.blob + p.proj2_b_off + (long long)l * p.layer_stride + cta * 8 + warp);
 #if GV_PP_COUNTER
-                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near); GV_NBAR(1);
+                    hop_wait(hc + HC_PP * GV_HOP_STRIDE, (lc + 1u) * (unsigned)G, tid, tmask, settle, hold_c, near);
 #endif
                     stamp(ts + 10);
                     {   // load q: 16 bytes {v, tag, v, tag} of source CTA q / 4, outputs 2 (q % 4), +1; three rounds in flight
@@ -888,7 +881,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                         }
                     }
                     if (hold_c && tid == 0) *hold_c = 0;  // hop data is in registers: the producer may stream again
-                    BAR1(); GV_NBAR(1);
+                    BAR1();
                     {
                         float s = 0.0f;
                         for (int c = lane; c < G; c += 32) s += gat[c * 8 + warp];
@@ -916,7 +909,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
 #if GV_ATOMIC_RED
                 lat = xnext;
 #else
-                hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, settle, hold_c, near); GV_NBAR(1);
+                hop_wait(hc + HC_X2 * GV_HOP_STRIDE, lc * (unsigned)n_red, tid, tmask, settle, hold_c, near);
                 ld_tagged_vec_u<4>(p.x2, 4 * tid, xvalid, tg - (uint32_t)GV_TAGS_PER_LAYER + TG_X2, tmask, &lat.x);
                 if (!xvalid) lat = make_float4(0.f, 0.f, 0.f, 0.f);
 #endif
@@ -924,10 +917,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                 stamp(ts + 0);
                 const float* lnp = tile_wait(ring, cs, cs.gt, lane);  // all warps read the parameter tile
                 ln_quad(lat, xvalid, D, lnp, lnp + D, red, tid);
-                BAR1(); GV_NBAR(1);  // `red` is reused by the second LayerNorm
+                BAR1();  // `red` is reused by the second LayerNorm
                 ln_quad(lat, xvalid, D, lnp + 2 * D, lnp + 3 * D, red, tid);
                 if (xvalid) *reinterpret_cast<float4*>(xo + 4 * tid) = lat;
-                BAR1(); GV_NBAR(1);
+                BAR1();
                 if (warp == 0) tile_release(ring, cs.gt, lane, 4u);
                 cs.gt += 1u;
 #if !GV_PRE_HEAD
@@ -939,7 +932,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
                 stamp(ts + 1);
                 hop_arrive(hc + HC_LG * GV_HOP_STRIDE, tid);
                 t_lg += (unsigned)G;
-                hop_wait(hc + HC_LG * GV_HOP_STRIDE, t_lg, tid, tmask, settle, hold_c, near); GV_NBAR(1);
+                hop_wait(hc + HC_LG * GV_HOP_STRIDE, t_lg, tid, tmask, settle, hold_c, near);
                 for (int e0 = 0; e0 < p.Vpad; e0 += 2 * MEGA_CONSUMERS) {  // uniform trip count; lg holds Vpad (even) tagged words
                     const int e = e0 + 2 * tid;
                     const bool v0 = e < p.V, v1 = e + 1 < p.V;
@@ -965,7 +958,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
             for (int e = tid; e < p.V; e += MEGA_CONSUMERS) slog[e] = ldcg(p.pend_logits + e);
             if (xvalid) lat = ldcg4(p.pend_latent + 4 * tid);
         }
-        BAR1(); GV_NBAR(1);  // slog complete; attention / gather scratch (aliasing `keys`) is dead
+        BAR1();  // slog complete; attention / gather scratch (aliasing `keys`) is dead
         // ------------- sample + emit (every CTA computes the same token) -------------
         int tok = sample_token([&](int e) { return slog[e]; }, seen, scfg, p.noise ? p.noise + (size_t)i * p.V : nullptr, p.seed,
                                (uint32_t)n, 0u, keys, fscr, iscr, tid, [] { BAR1(); });
@@ -987,7 +980,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
         if (!p.ignore_eos && tok == p.stop_token) finished = 1;
         n += 1;
         emitted += 1;
-        BAR1(); GV_NBAR(1);  // seen[] update visible to the next step's sampler; slog / keys free
+        BAR1();  // seen[] update visible to the next step's sampler; slog / keys free
         if (finished || n >= p.max_total) {
             done = 1;
             break;
@@ -1000,7 +993,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(MegaParams
         ctl[0] = 1;
     }
     if (cta == 0) {
-        BAR1(); GV_NBAR(1);
+        BAR1();
         for (int q = tid; q < p.Vpad; q += MEGA_CONSUMERS) p.seen_out[q] = seen[q];
         if (tid == 0) {
             GenState* so = p.st_out;
@@ -1068,8 +1061,7 @@ cudaError_t launch_decode_mega(const MegaParams& p, int grid, cudaStream_t st) {
 
 #ifdef GV_PROG
 extern "C" int genvc_debug_prog_copy(unsigned* pinned_host, void* stream) {
-    cudaMemcpyFromSymbolAsync(pinned_host + 160 * 8 * 4 + 160 * 256, gv::mega1::g_slip, sizeof(unsigned) * (8 + 8 * 64), 0, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
-    cudaMemcpyFromSymbolAsync(pinned_host + 160 * 8 * 4, gv::g_progt, sizeof(unsigned) * 160 * 256, 0, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    cudaMemcpyFromSymbolAsync(pinned_host + 160 * 8 * 4, gv::mega1::g_slip, sizeof(unsigned) * (8 + 8 * 64), 0, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
     return (int)cudaMemcpyFromSymbolAsync(pinned_host, gv::g_prog, sizeof(unsigned) * 160 * 8 * 4, 0, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
 }
 #endif

@@ -29,15 +29,15 @@ __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.0f ?
 // y[b, co, t] = epi( bias[co] + sum_ci sum_j w[ci][j][co] * lrelu(x[b, ci, t + j * dil - pad]) )
 __global__ void __launch_bounds__(VC_THREADS)
 conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-              const float* __restrict__ res, float* __restrict__ y, int Cin, int Cout, int T, int K, int dil, int pad,
-              float pre_slope, int accumulate, float out_scale, int act_tanh, int ksplit, float* __restrict__ scratch) {
+              const float* __restrict__ res, float* __restrict__ y, int Cin, int Cout, int T, int To, int K, int dil, int pad,
+              int stride, float pre_slope, int accumulate, float out_scale, int act_out, int ksplit, float* __restrict__ scratch) {
     extern __shared__ float sm[];
     const int halo = (K - 1) * dil;
-    const int XW = VC_T_T + halo;             // staged samples per input channel
+    const int XW = (VC_T_T - 1) * stride + halo + 1;  // staged samples per input channel (T = input, To = output length)
     float* xin = sm;                          // [VC_CI_C][XW]
     float* ws = sm + VC_CI_C * XW;            // [VC_CI_C][K][VC_CO_T]
     const int tid = threadIdx.x;
-    const int cg = tid >> 5, tg = tid & 31;   // channel group (warp), sample group (lane)
+    const int cg = tid >> 5, tg = tid & 31;   // channel group (warp: 4 channels), lane: outputs t0 + tg + {0, 32, 64, 96}
     // split over the input channels (small layers: too few output tiles to fill the GPU): slice ks of ksplit writes its
     // partial sums to scratch[ks][b][co][t]; splitk_epilogue_kernel adds the slices in a fixed order
     const int t0 = blockIdx.x * VC_T_T, co0 = blockIdx.y * VC_CO_T, b = blockIdx.z / ksplit, ks = blockIdx.z % ksplit;
@@ -53,43 +53,40 @@ conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
     // Software pipeline: the global loads of round r + 1 are issued into registers before round r is computed, and
     // written to shared memory after it -- a block has few rounds' worth of parallelism (one block per SM at streaming
     // sizes), so an exposed L2 / HBM latency per round would dominate the layer.
-    constexpr int XMAX = 16, WMAX = 24;  // staged elements per thread (host checks the bounds)
-    const int nx = VC_CI_C * XW, nw = VC_CI_C * K * VC_CO_T;
-    float xreg[XMAX], wreg[WMAX];
+    // Staging layout: warp cg stages input channels cg and cg + 8 of the round (lane = sample, 32 apart) and their K weight
+    // rows (lane = output channel) -- no index arithmetic per element.  Bounds (host-checked): XW <= 9 * 32, K <= 12.
+    constexpr int XM = 9, KM = 12, CH = VC_CI_C / 8;
+    float xreg[CH][XM], wreg[CH][KM];
     auto fetch = [&](int c0) {
 #pragma unroll
-        for (int r = 0; r < XMAX; ++r) {
-            const int e = tid + r * VC_THREADS;
-            float v = 0.0f;
-            if (e < nx) {
-                const int ci = e / XW, s = e - ci * XW;
-                const int t = t0 + s - pad;
-                if (c0 + ci < c_end && t >= 0 && t < T) v = lrelu(__ldg(xb + (size_t)(c0 + ci) * T + t), pre_slope);
-            }
-            xreg[r] = v;
-        }
+        for (int h = 0; h < CH; ++h) {
+            const int ci = c0 + cg + 8 * h;
+            const bool cok = ci < c_end;
+            const float* xrow = xb + (size_t)ci * T;
 #pragma unroll
-        for (int r = 0; r < WMAX; ++r) {
-            const int e = tid + r * VC_THREADS;
-            float v = 0.0f;
-            if (e < nw) {
-                const int co = e % VC_CO_T, cj = e / VC_CO_T;  // cj = ci * K + j
-                const int ci = cj / K;
-                if (c0 + ci < c_end && co0 + co < Cout) v = __ldg(w + ((size_t)(c0 + ci) * K + (cj - ci * K)) * Cout + co0 + co);
+            for (int m = 0; m < XM; ++m) {
+                const int sidx = tg + 32 * m;
+                const int t = t0 * stride + sidx - pad;
+                xreg[h][m] = (cok && sidx < XW && t >= 0 && t < T) ? lrelu(__ldg(xrow + t), pre_slope) : 0.0f;
             }
-            wreg[r] = v;
+            const float* wrow = w + (size_t)ci * K * Cout + co0 + tg;
+            const bool wok = cok && co0 + tg < Cout;
+#pragma unroll
+            for (int j = 0; j < KM; ++j) wreg[h][j] = (wok && j < K) ? __ldg(wrow + (size_t)j * Cout) : 0.0f;
         }
     };
     auto commit = [&]() {
 #pragma unroll
-        for (int r = 0; r < XMAX; ++r) {
-            const int e = tid + r * VC_THREADS;
-            if (e < nx) xin[e] = xreg[r];
-        }
+        for (int h = 0; h < CH; ++h) {
+            const int cl = cg + 8 * h;
 #pragma unroll
-        for (int r = 0; r < WMAX; ++r) {
-            const int e = tid + r * VC_THREADS;
-            if (e < nw) ws[e] = wreg[r];
+            for (int m = 0; m < XM; ++m) {
+                const int sidx = tg + 32 * m;
+                if (sidx < XW) xin[cl * XW + sidx] = xreg[h][m];
+            }
+#pragma unroll
+            for (int j = 0; j < KM; ++j)
+                if (j < K) ws[(cl * K + j) * VC_CO_T + tg] = wreg[h][j];
         }
     };
     if (c_begin < c_end) fetch(c_begin);
@@ -99,12 +96,15 @@ conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
         if (c0 + VC_CI_C < c_end) fetch(c0 + VC_CI_C);
 #pragma unroll 2
         for (int ci = 0; ci < VC_CI_C; ++ci) {
-            const float* xr = xin + ci * XW + tg * 4;
+            // the thread's four outputs are t0 + tg + 32 q: for a fixed q the 32 lanes read consecutive words (no bank
+            // conflicts; a 4-consecutive-outputs layout makes every one of these loads a 4-way conflict and the kernel
+            // shared-memory bound)
+            const float* xr = xin + ci * XW + tg * stride;
             const float* wr = ws + ci * K * VC_CO_T + cg * 4;
             for (int j = 0; j < K; ++j) {
                 const float4 wv = *reinterpret_cast<const float4*>(wr + j * VC_CO_T);
                 const float* xp = xr + j * dil;
-                const float x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
+                const float x0 = xp[0], x1 = xp[32 * stride], x2 = xp[64 * stride], x3 = xp[96 * stride];
                 acc[0][0] = fmaf(wv.x, x0, acc[0][0]); acc[0][1] = fmaf(wv.x, x1, acc[0][1]);
                 acc[0][2] = fmaf(wv.x, x2, acc[0][2]); acc[0][3] = fmaf(wv.x, x3, acc[0][3]);
                 acc[1][0] = fmaf(wv.y, x0, acc[1][0]); acc[1][1] = fmaf(wv.y, x1, acc[1][1]);
@@ -123,31 +123,32 @@ conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
         for (int i = 0; i < 4; ++i) {
             const int co = co0 + cg * 4 + i;
             if (co >= Cout) continue;
-            float* prow = scratch + (((size_t)ks * Bn + b) * Cout + co) * T;
+            float* prow = scratch + (((size_t)ks * Bn + b) * Cout + co) * To;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int t = t0 + tg * 4 + q;
-                if (t < T) prow[t] = acc[i][q];
+                const int t = t0 + tg + 32 * q;
+                if (t < To) prow[t] = acc[i][q];
             }
         }
         return;
     }
-    // epilogue: bias, residual, accumulate / scale, tanh
+    // epilogue: bias, residual, accumulate / scale, output activation (1 tanh, 2 relu)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int co = co0 + cg * 4 + i;
         if (co >= Cout) continue;
         const float bv = bias ? __ldg(bias + co) : 0.0f;
-        const size_t row = ((size_t)b * Cout + co) * T;
+        const size_t row = ((size_t)b * Cout + co) * To;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int t = t0 + tg * 4 + q;
-            if (t >= T) continue;
+            const int t = t0 + tg + 32 * q;
+            if (t >= To) continue;
             float v = acc[i][q] + bv;
             if (res) v += res[row + t];
             if (accumulate) v += y[row + t];
             v *= out_scale;
-            if (act_tanh) v = tanhf(v);
+            if (act_out == 1) v = tanhf(v);
+            else if (act_out == 2) v = fmaxf(v, 0.0f);
             y[row + t] = v;
         }
     }
@@ -178,7 +179,7 @@ conv_transpose1d_kernel(const float* __restrict__ x, const float* __restrict__ w
     int kk0[4], sr0[4];  // first tap and its (staged) input index for each of the thread's four outputs
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int tp = t0 + tg * 4 + q + pad;
+        const int tp = t0 + tg + 32 * q + pad;
         kk0[q] = tp % stride;
         sr0[q] = tp / stride - s_lo;
     }
@@ -224,7 +225,7 @@ conv_transpose1d_kernel(const float* __restrict__ x, const float* __restrict__ w
             float* prow = scratch + (((size_t)ks * Bn + b) * Cout + co) * Tout;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int t = t0 + tg * 4 + q;
+                const int t = t0 + tg + 32 * q;
                 if (t < Tout) prow[t] = acc[i][q];
             }
         }
@@ -238,10 +239,67 @@ conv_transpose1d_kernel(const float* __restrict__ x, const float* __restrict__ w
         const size_t row = ((size_t)b * Cout + co) * Tout;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int t = t0 + tg * 4 + q;
+            const int t = t0 + tg + 32 * q;
             if (t < Tout) y[row + t] = acc[i][q] + bv;
         }
     }
+}
+
+// Nearest codebook entry (layers/dvae.py:84-88, Quantize.forward at inference): for every (b, t)
+//   dist[n] = sum_c f[c]^2 - 2 * sum_c f[c] * E[c][n] + sum_c E[c][n]^2 ;  code = argmax_n(-dist[n]), first index on ties.
+// x is the encoder output as it leaves the last convolution, [B, dim, T] (the reference permutes to [B, T, dim] first).
+// One block per (b, t); thread n owns code n (strided if n_embed > blockDim); E is [dim][n_embed], read coalesced.
+__global__ void __launch_bounds__(256)
+codebook_argmin_kernel(const float* __restrict__ x, const float* __restrict__ embed, long long* __restrict__ codes, int dim,
+                       int n_embed, int T) {
+    extern __shared__ float f[];  // [dim] feature vector of this position, then reduction scratch
+    __shared__ float s_val[256];
+    __shared__ int s_idx[256];
+    const int b = blockIdx.x / T, t = blockIdx.x % T, tid = threadIdx.x;
+    float part = 0.0f;
+    for (int c = tid; c < dim; c += blockDim.x) {
+        const float v = x[((size_t)b * dim + c) * T + t];
+        f[c] = v;
+        part += v * v;
+    }
+    s_val[tid] = part;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (tid < o) s_val[tid] += s_val[tid + o];
+        __syncthreads();
+    }
+    const float f2 = s_val[0];
+    __syncthreads();
+    float best = -INFINITY;
+    int best_n = 0x7fffffff;
+    for (int n = tid; n < n_embed; n += blockDim.x) {
+        float dot = 0.0f, e2 = 0.0f;
+        for (int c = 0; c < dim; ++c) {
+            const float e = __ldg(embed + (size_t)c * n_embed + n);
+            dot = fmaf(f[c], e, dot);
+            e2 = fmaf(e, e, e2);
+        }
+        const float neg = -((f2 - 2.0f * dot) + e2);
+        if (neg > best) {  // n ascends: the first maximum is kept
+            best = neg;
+            best_n = n;
+        }
+    }
+    s_val[tid] = best;
+    s_idx[tid] = best_n;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (tid < o) {
+            const float v = s_val[tid + o];
+            const int i = s_idx[tid + o];
+            if (v > s_val[tid] || (v == s_val[tid] && i < s_idx[tid])) {
+                s_val[tid] = v;
+                s_idx[tid] = i;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) codes[(size_t)b * T + t] = s_idx[0];
 }
 
 // sum of the ksplit partial slices in slice order, then the same epilogue as the unsplit kernels
@@ -257,7 +315,8 @@ splitk_conv_epilogue_kernel(const float* __restrict__ scratch, const float* __re
         if (res) v += res[e];
         if (accumulate) v += y[e];
         v *= out_scale;
-        if (act_tanh) v = tanhf(v);
+        if (act_tanh == 1) v = tanhf(v);
+        else if (act_tanh == 2) v = fmaxf(v, 0.0f);
         y[e] = v;
     }
 }
@@ -276,29 +335,31 @@ static int pick_ksplit(int tiles, int Cin, size_t out_elems, size_t scratch_floa
 // C ABI
 // ---------------------------------------------------------------------------------------------------------------------
 extern "C" int genvc_conv1d(const float* x, const float* w, const float* bias, const float* residual, float* y, int B, int Cin,
-                            int Cout, int T, int K, int dilation, int padding, float pre_slope, int accumulate, float out_scale,
-                            int act_tanh, float* scratch, uint64_t scratch_floats, void* stream) {
-    if (!x || !w || !y || B <= 0 || Cin <= 0 || Cout <= 0 || T <= 0 || K <= 0 || K > 31 || dilation <= 0 || padding < 0)
+                            int Cout, int T, int K, int dilation, int padding, int stride, float pre_slope, int accumulate,
+                            float out_scale, int act_out, float* scratch, uint64_t scratch_floats, void* stream) {
+    if (!x || !w || !y || B <= 0 || Cin <= 0 || Cout <= 0 || T <= 0 || K <= 0 || K > 12 || dilation <= 0 || padding < 0 ||
+        stride <= 0 || stride > 2 || act_out < 0 || act_out > 2)
         return GENVC_E_INVALID;
-    if (2 * padding != (K - 1) * dilation) return GENVC_E_INVALID;  // "same" convolutions only (utils.py:174 get_padding)
-    // register staging of the kernel: 16 input and 24 weight elements per thread and round
-    if (gv::VC_CI_C * (gv::VC_T_T + (K - 1) * dilation) > 16 * gv::VC_THREADS || gv::VC_CI_C * K * gv::VC_CO_T > 24 * gv::VC_THREADS)
-        return GENVC_E_UNSUPPORTED;
-    const size_t smem = ((size_t)gv::VC_CI_C * (gv::VC_T_T + (K - 1) * dilation) + (size_t)gv::VC_CI_C * K * gv::VC_CO_T) * sizeof(float);
+    const int To = (T + 2 * padding - dilation * (K - 1) - 1) / stride + 1;  // torch.nn.Conv1d
+    if (To <= 0 || (residual && To != T)) return GENVC_E_INVALID;
+    const int XW = (gv::VC_T_T - 1) * stride + (K - 1) * dilation + 1;
+    if (XW > 9 * 32 || K > 12) return GENVC_E_UNSUPPORTED;  // register staging of the kernel (conv1d_kernel: XM, KM)
+    const size_t smem = ((size_t)gv::VC_CI_C * XW + (size_t)gv::VC_CI_C * K * gv::VC_CO_T) * sizeof(float);
     if (smem > 200 * 1024) return GENVC_E_INVALID;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(gv::conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return GENVC_E_CUDA;
-    dim3 grid((T + gv::VC_T_T - 1) / gv::VC_T_T, (Cout + gv::VC_CO_T - 1) / gv::VC_CO_T, B);
-    const size_t out_elems = (size_t)B * Cout * T;
+    dim3 grid((To + gv::VC_T_T - 1) / gv::VC_T_T, (Cout + gv::VC_CO_T - 1) / gv::VC_CO_T, B);
+    const size_t out_elems = (size_t)B * Cout * To;
     const int ks = gv::pick_ksplit((int)(grid.x * grid.y * grid.z), Cin, out_elems, scratch ? (size_t)scratch_floats : 0);
     grid.z = B * ks;
-    gv::conv1d_kernel<<<grid, gv::VC_THREADS, smem, (cudaStream_t)stream>>>(x, w, bias, residual, y, Cin, Cout, T, K, dilation, padding,
-                                                                             pre_slope, accumulate, out_scale, act_tanh, ks, scratch);
+    gv::conv1d_kernel<<<grid, gv::VC_THREADS, smem, (cudaStream_t)stream>>>(x, w, bias, residual, y, Cin, Cout, T, To, K, dilation,
+                                                                             padding, stride, pre_slope, accumulate, out_scale,
+                                                                             act_out, ks, scratch);
     if (ks > 1) {
         const int blocks = (int)std::min<size_t>((out_elems + 255) / 256, 1184);
-        gv::splitk_conv_epilogue_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scratch, bias, residual, y, ks, B, Cout, T, accumulate,
-                                                                                  out_scale, act_tanh);
+        gv::splitk_conv_epilogue_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scratch, bias, residual, y, ks, B, Cout, To, accumulate,
+                                                                                  out_scale, act_out);
     }
     return cudaGetLastError() == cudaSuccess ? GENVC_OK : GENVC_E_CUDA;
 }
@@ -325,5 +386,12 @@ extern "C" int genvc_conv_transpose1d(const float* x, const float* w, const floa
         const int blocks = (int)std::min<size_t>((out_elems + 255) / 256, 1184);
         gv::splitk_conv_epilogue_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scratch, bias, nullptr, y, ks, B, Cout, Tout, 0, 1.0f, 0);
     }
+    return cudaGetLastError() == cudaSuccess ? GENVC_OK : GENVC_E_CUDA;
+}
+
+extern "C" int genvc_codebook_argmin(const float* x, const float* embed, int64_t* codes, int B, int dim, int n_embed, int T, void* stream) {
+    if (!x || !embed || !codes || B <= 0 || dim <= 0 || n_embed <= 0 || T <= 0 || dim > 8192) return GENVC_E_INVALID;
+    gv::codebook_argmin_kernel<<<B * T, 256, (size_t)dim * sizeof(float), (cudaStream_t)stream>>>(x, embed, reinterpret_cast<long long*>(codes),
+                                                                                                    dim, n_embed, T);
     return cudaGetLastError() == cudaSuccess ? GENVC_OK : GENVC_E_CUDA;
 }

@@ -9,8 +9,9 @@ keeps working without coqpit.
 
 Stages outside this path (ContentVec, content-DVAE, mel front-end, HiFi-GAN; SURVEY.md §2 #9-#11,
 #16) are *attachment points* on the returned model: assign the reference's own modules to
-``model.content_extractor``, ``model.content_dvae``, ``model.hifigan`` (built on the CUDA library automatically when the
-checkpoint holds ``hifigan.*`` weights: ``genvc_b200/vocoder.py``) and
+``model.content_extractor``, ``model.content_dvae`` and ``model.hifigan`` (the last two are built on the CUDA library
+automatically when the checkpoint holds ``content_dvae.*`` / ``hifigan.*`` weights: ``genvc_b200/content_dvae.py``,
+``genvc_b200/vocoder.py``) and
 ``model.torch_mel_spectrogram_style_encoder`` to run the full pipeline.
 """
 from __future__ import annotations
@@ -148,7 +149,21 @@ def model_from_checkpoint(ckpt_states: dict, device, max_batch: int = 1, max_mel
     model.gpt.to(device)
     model.gpt.init_gpt_for_inference()
     attach_cuda_hifigan(model, ckpt_states.get("model") or {}, ckpt_states["config"])
+    attach_cuda_content_dvae(model, ckpt_states.get("model") or {}, ckpt_states["config"])
     return model, config
+
+
+def attach_cuda_content_dvae(model, state_dict: dict, raw_config) -> bool:
+    """``content_dvae.*`` weights in the checkpoint -> the tokeniser runs on the CUDA library (``genvc_b200/content_dvae.py``,
+    built from ``config.content_dvae_config`` like ``trainers/hifigan_trainer.py:149-160``)."""
+    sd = {k[len("content_dvae."):]: v for k, v in state_dict.items() if k.startswith("content_dvae.")}
+    if "codebook.embed" not in sd or torch.device(model.device).type != "cuda":
+        return False
+    from ..content_dvae import DiscreteVAE
+
+    dc = raw_config.get("content_dvae_config", {}) if isinstance(raw_config, dict) else getattr(raw_config, "content_dvae_config", {})
+    model.content_dvae = DiscreteVAE.from_config(dc or {}, device=model.device).load_state_dict(sd)
+    return True
 
 
 def attach_cuda_hifigan(model, state_dict: dict, raw_config) -> bool:

@@ -179,3 +179,37 @@ def synth_hifigan_state(seed: int = 77, weight_norm: bool = True, **overrides) -
             sd[name + ".weight"] = v
         sd[name + ".bias"] = bias
     return sd
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# content-DVAE tokeniser (the stage before the path): synthetic weights under the reference's state-dict names
+# ------------------------------------------------------------------------------------------------------------------
+CONTENT_DVAE_DEFAULTS = dict(channels=256, num_tokens=256, codebook_dim=512, hidden_dim=512, num_resnet_blocks=3, kernel_size=3,
+                             num_layers=2)  # train_content_dvae.py:32-38
+
+
+def synth_dvae_state(seed: int = 55, **overrides) -> Dict[str, torch.Tensor]:
+    """Encoder + codebook of ``layers/dvae.py::DiscreteVAE(positional_dims=1)`` (keys ``encoder.N...``, ``codebook.embed``);
+    the decoder is not part of inference and is left out (load with strict=False)."""
+    cfg = dict(CONTENT_DVAE_DEFAULTS, **overrides)
+    gen = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, cout, cin, k, gain=1.4):
+        sd[name + ".weight"] = torch.randn(cout, cin, k, generator=gen) * (gain / (cin * k) ** 0.5)
+        sd[name + ".bias"] = torch.randn(cout, generator=gen) * 0.05
+
+    chans = [cfg["channels"]] + [cfg["hidden_dim"] * 2 ** i for i in range(cfg["num_layers"])]
+    i = 0
+    for cin, cout in zip(chans[:-1], chans[1:]):
+        conv(f"encoder.{i}.0", cout, cin, cfg["kernel_size"])
+        i += 1
+    inner = chans[-1]
+    for _ in range(cfg["num_resnet_blocks"]):
+        conv(f"encoder.{i}.net.0", inner, inner, 3)
+        conv(f"encoder.{i}.net.2", inner, inner, 3)
+        conv(f"encoder.{i}.net.4", inner, inner, 1, gain=0.5)  # keeps the residual stream O(1) through the blocks
+        i += 1
+    conv(f"encoder.{i}", cfg["codebook_dim"], inner, 1, gain=1.0)
+    sd["codebook.embed"] = torch.randn(cfg["codebook_dim"], cfg["num_tokens"], generator=gen)
+    return sd

@@ -128,7 +128,7 @@ class HiFiGAN:
         self.launches += 1
         self._check(self.lib.genvc_conv1d(x.data_ptr(), c.w.data_ptr(), c.b.data_ptr() if c.b is not None else None,
                                           residual.data_ptr() if residual is not None else None, y.data_ptr(), B, c.cin, c.cout, T,
-                                          c.k, c.dil, c.pad, float(slope), int(accumulate), float(scale), int(tanh),
+                                          c.k, c.dil, c.pad, 1, float(slope), int(accumulate), float(scale), int(tanh),
                                           self._scratch.data_ptr(), self._scratch.numel(), st), name)
 
     def _up(self, name: str, x, y, Tin: int, B: int, slope: float, st=None):

@@ -206,9 +206,10 @@ int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, in
  * (reference: Conv1d weight [Cout][Cin][K] -> permute(1,2,0); ConvTranspose1d weight [Cin][Cout][K] -> permute(0,2,1)),
  * weight norm already folded (w = g * v / ||v||).
  *
- * genvc_conv1d: "same" convolution, stride 1 (2 * padding == (K - 1) * dilation):
- *   v = bias[co] + sum_ci sum_j w[ci][j][co] * lrelu(x[b][ci][t + j*dilation - padding], pre_slope)   (pre_slope 1 = no activation)
- *   v += residual[b][co][t] if residual;  v += y[b][co][t] if accumulate;  v *= out_scale;  v = tanh(v) if act_tanh;  y = v
+ * genvc_conv1d: torch.nn.Conv1d(Cin, Cout, K, stride 1|2, padding, dilation); To = (T + 2*padding - dilation*(K-1) - 1) / stride + 1
+ *   v = bias[co] + sum_ci sum_j w[ci][j][co] * lrelu(x[b][ci][t*stride + j*dilation - padding], pre_slope)   (pre_slope 1 = none)
+ *   v += residual[b][co][t] if residual (needs To == T);  v += y[b][co][t] if accumulate;  v *= out_scale;
+ *   act_out: 0 none, 1 tanh, 2 relu;  y = v
  *   — i.e. `xt = c(leaky_relu(x)); x = xt + x` of ResBlock2 (layers/hifigan.py:147-152) is ONE call, and
  *   `xs += resblock(x)`, `x = xs / num_kernels` (:216-221) ride in the epilogue of each block's last conv.
  * genvc_conv_transpose1d: torch.nn.ConvTranspose1d(Cin, Cout, K, stride, padding) on lrelu(x, pre_slope)
@@ -217,11 +218,18 @@ int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, in
  *   over their input channels into up to scratch_floats / (B*Cout*T) slices that are summed in a fixed order (results do
  *   not depend on timing); NULL keeps every layer in one pass. */
 int genvc_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, const float* residual_dev, float* y_dev,
-                 int B, int Cin, int Cout, int T, int K, int dilation, int padding, float pre_slope, int accumulate,
-                 float out_scale, int act_tanh, float* scratch_dev, uint64_t scratch_floats, void* stream);
+                 int B, int Cin, int Cout, int T, int K, int dilation, int padding, int stride, float pre_slope,
+                 int accumulate, float out_scale, int act_out, float* scratch_dev, uint64_t scratch_floats, void* stream);
 int genvc_conv_transpose1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* y_dev, int B, int Cin,
                            int Cout, int Tin, int K, int stride, int padding, float pre_slope, float* scratch_dev,
                            uint64_t scratch_floats, void* stream);
+
+/* ---- the stage before the path: content-DVAE tokeniser ----
+ * DiscreteVAE.get_codebook_indices (layers/dvae.py:324-331): encoder = strided convolutions + ReLU, ResBlocks, 1x1
+ * convolution (genvc_conv1d above), then Quantize.forward (layers/dvae.py:84-88): for the encoder output x [B, dim, T]
+ * and the codebook embed [dim, n_embed]:  codes[b][t] = argmax_n -( |f|^2 - 2 f.E[:,n] + |E[:,n]|^2 ), first index on ties. */
+int genvc_codebook_argmin(const float* x_dev, const float* embed_dev, int64_t* codes_dev, int B, int dim, int n_embed, int T,
+                          void* stream);
 
 /* Post-mortem aid (tools/hang_dump.py): byte offsets inside the workspace of the fused decode kernel's exchange buffers and
  * arrival counters: out[0..11] = xq, att_o, att_ml, x1, pp, x2, lg, hops, sbuf offsets, then grid, counter stride (words),

@@ -104,9 +104,9 @@ def test_conv_entry_points_reject_bad_arguments(cuda_device):
     x = torch.zeros(1, 8, 16, device=cuda_device)
     w = torch.zeros(8, 3, 8, device=cuda_device)
     y = torch.zeros(1, 8, 16, device=cuda_device)
-    # padding that is not "same"
-    assert lib.genvc_conv1d(x.data_ptr(), w.data_ptr(), None, None, y.data_ptr(), 1, 8, 8, 16, 3, 1, 0, 1.0, 0, 1.0, 0, None, 0, None) < 0
-    assert lib.genvc_conv1d(None, w.data_ptr(), None, None, y.data_ptr(), 1, 8, 8, 16, 3, 1, 1, 1.0, 0, 1.0, 0, None, 0, None) < 0
+    # unsupported stride
+    assert lib.genvc_conv1d(x.data_ptr(), w.data_ptr(), None, None, y.data_ptr(), 1, 8, 8, 16, 3, 1, 0, 3, 1.0, 0, 1.0, 0, None, 0, None) < 0
+    assert lib.genvc_conv1d(None, w.data_ptr(), None, None, y.data_ptr(), 1, 8, 8, 16, 3, 1, 1, 1, 1.0, 0, 1.0, 0, None, 0, None) < 0
     assert lib.genvc_conv_transpose1d(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), 1, 8, 8, 0, 3, 2, 0, 1.0, None, 0, None) < 0
 
 

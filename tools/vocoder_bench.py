@@ -62,3 +62,22 @@ for label, T in (("chunk_8_tokens", 32), ("segment_1s", 94), ("segment_6s", 563)
     out[label] = r
 out["launches_per_forward"] = 1 + 3 + 18 + 1
 print(json.dumps(out))
+
+# ---- content-DVAE tokeniser (the stage before the path)
+from genvc_b200.content_dvae import DiscreteVAE
+from genvc_b200.synth import synth_dvae_state
+dv = DiscreteVAE.from_config({}, device=dev).load_state_dict(synth_dvae_state(55))
+dres = {}
+for label, T in (("segment_1s", 50), ("segment_6s", 300)):
+    x = torch.randn(1, 256, T, device=dev)
+    for _ in range(3):
+        dv.get_codebook_indices(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        dv.get_codebook_indices(x)
+    e1.record()
+    torch.cuda.synchronize()
+    dres[label] = {"frames": T, "codes": (T + 3) // 4, "ms": round(e0.elapsed_time(e1) / a.reps, 4)}
+print(json.dumps({"content_dvae": dres}))
