@@ -17,6 +17,7 @@
 //     through a tagged word; every CTA reads the B tokens for the next step's embeddings.
 #define GV_RING_NSLOT GV_BATCH_NSLOT
 #define GV_MEGA_NS megab
+#define GV_UNIFORM_TILE_WAIT 1  // consumer warps never split on a wait (mega_dev.cuh: tile_ready_wait_u, ld_tagged_vec_u)
 #include "mega_dev.cuh"
 
 namespace gv {
@@ -216,7 +217,8 @@ __device__ __forceinline__ void load_rows(const float* buf, uint32_t tag, float*
             if (r0 + q < nb) {
                 const float* p = buf + 2 * ((size_t)(r0 + q) * D + 4 * tid);
                 uint32_t spins = 0;
-                while (!(tags_ok(a[q], tag, 0xffffffffu) && tags_ok(b[q], tag, 0xffffffffu))) {
+                // the warp leaves the poll as one (4 * tid < D is warp-uniform: D is a multiple of 128)
+                while (!__all_sync(0xffffffffu, tags_ok(a[q], tag, 0xffffffffu) && tags_ok(b[q], tag, 0xffffffffu))) {
                     GV_SPIN(spins, __LINE__, 0u, 0u);
                     a[q] = ld_x16(p);
                     b[q] = ld_x16(p + 4);
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_batch_kernel(MegaParam
                                         if (s0 + q < nsplit) {
                                             const int it = rh * nsplit + s0 + q;
                                             uint32_t spins = 0;
-                                            while (!(tags_ok(a[q], tga, tmask) && b[q].y == tga)) {
+                                            while (!__all_sync(0xffffffffu, tags_ok(a[q], tga, tmask) && b[q].y == tga)) {  // tid < HD: whole warps
                                                 GV_SPIN(spins, __LINE__, 0u, 0u);
                                                 a[q] = ld_x16(p.att_ml + 2 * (size_t)(it * 2));
                                                 b[q] = ld_x8(p.att_o + 2 * (size_t)(it * HD + tid));
