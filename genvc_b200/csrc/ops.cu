@@ -503,7 +503,109 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnArgs a, const int* s
     }
 }
 
+// Few query rows (the prefill of a 1 s segment is 48 rows x 4 heads): one CTA per (query row, head, batch element) instead of
+// one per 8 rows -- 192 CTAs instead of 24 -- and no shared-memory staging: warp w takes keys w, w + 8, ... straight from
+// L2 (a K / V row is one coalesced 128-byte-per-8-lanes read), lanes split the head dimension, one shuffle tree per key,
+// online softmax per warp; the eight per-warp (max, sum, o[hd]) meet in shared memory behind one barrier and are merged in
+// warp order by thread d < hd.  16 us -> ~4 us for the 48-row prefill; K / V are re-read per query row, so the tiled kernel
+// above keeps the long-M cases (latent pass, perceiver).
+template <int HD>
+__global__ void __launch_bounds__(256) attention_row_kernel(AttnArgs a, const int* skip) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (skip && *skip) return;
+    constexpr int DPL = HD / 32;  // consecutive dims per lane
+    __shared__ float s_m[8], s_l[8];
+    __shared__ __align__(16) float s_o[8][HD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const float* Qb = a.Q + (size_t)b * a.q_bs + (size_t)h * a.q_hs + (size_t)i * a.q_rs + lane * DPL;
+    const float* Kb = a.K + (size_t)b * a.k_bs + (size_t)h * a.k_hs + lane * DPL;
+    const float* Vb = a.V + (size_t)b * a.v_bs + (size_t)h * a.v_hs + lane * DPL;
+    const int my_keys = a.causal ? min(a.n_keys, a.pos0 + i + 1) : a.n_keys;
+    auto load = [&](const float* p, float* r) {
+        if constexpr (DPL % 4 == 0) {
+#pragma unroll
+            for (int c = 0; c < DPL; c += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(p + c);
+                r[c] = t.x; r[c + 1] = t.y; r[c + 2] = t.z; r[c + 3] = t.w;
+            }
+        } else if constexpr (DPL == 2) {
+            const float2 t = *reinterpret_cast<const float2*>(p);
+            r[0] = t.x; r[1] = t.y;
+        } else {
+            r[0] = *p;
+        }
+    };
+    float q[DPL], o[DPL];
+    load(Qb, q);
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) o[d] = 0.0f;
+    float m = -INFINITY, l = 0.0f;
+    for (int j = warp; j < my_keys; j += 16) {  // two keys of this warp in flight
+        const bool two = j + 8 < my_keys;
+        float k0[DPL], v0[DPL], k1[DPL], v1[DPL];
+        load(Kb + (size_t)j * a.k_rs, k0);
+        load(Vb + (size_t)j * a.v_rs, v0);
+        if (two) {
+            load(Kb + (size_t)(j + 8) * a.k_rs, k1);
+            load(Vb + (size_t)(j + 8) * a.v_rs, v1);
+        }
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) {
+            s0 = fmaf(q[d], k0[d], s0);
+            if (two) s1 = fmaf(q[d], k1[d], s1);
+        }
+#pragma unroll
+        for (int x = 16; x > 0; x >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, x);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, x);
+        }
+        s0 *= a.scale;
+        s1 = two ? s1 * a.scale : -INFINITY;
+        const float mn = fmaxf(m, fmaxf(s0, s1));
+        const float c = expf(m - mn), p0 = expf(s0 - mn), p1 = expf(s1 - mn);  // exp(-inf) = 0
+        l = l * c + p0 + p1;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) o[d] = fmaf(p1, two ? v1[d] : 0.0f, fmaf(p0, v0[d], o[d] * c));
+        m = mn;
+    }
+    if (lane == 0) {
+        s_m[warp] = m;
+        s_l[warp] = l;
+    }
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) s_o[warp][lane * DPL + d] = o[d];
+    __syncthreads();
+    if (tid < HD) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) M = fmaxf(M, s_m[w]);
+        float L = 0.0f, acc = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const float cw = expf(s_m[w] - M);  // warps without keys: exp(-inf) = 0
+            L = fmaf(s_l[w], cw, L);
+            acc = fmaf(s_o[w][tid], cw, acc);
+        }
+        a.O[(size_t)b * a.o_bs + (size_t)i * a.o_rs + (size_t)h * a.o_hs + tid] = acc / L;
+    }
+}
+
 cudaError_t launch_attention(const AttnArgs& a, const int* skip, cudaStream_t st, unsigned long long* nlaunch) {
+    static const bool rows_ok = [] { const char* e = getenv("GENVC_ATT_ROWS"); return !(e && e[0] == '0'); }();
+    if (rows_ok && a.M <= 64 && a.n_keys <= 4096) {
+        const dim3 g(a.M, a.H, a.B);
+        switch (a.hd) {
+            case 32: attention_row_kernel<32><<<g, 256, 0, st>>>(a, skip); break;
+            case 64: attention_row_kernel<64><<<g, 256, 0, st>>>(a, skip); break;
+            case 128: attention_row_kernel<128><<<g, 256, 0, st>>>(a, skip); break;
+            case 256: attention_row_kernel<256><<<g, 256, 0, st>>>(a, skip); break;
+            default: return cudaErrorInvalidValue;
+        }
+        GV_BUMP(nlaunch);
+        return cudaGetLastError();
+    }
     dim3 grid((a.M + 7) / 8, a.H, a.B);
     auto smem = [](int hd) { return (size_t)(8 * hd + 2 * 32 * (hd + 4)) * sizeof(float); };
     cudaError_t e = cudaSuccess;
