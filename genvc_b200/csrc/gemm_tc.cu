@@ -32,6 +32,7 @@
 #include <stdint.h>
 
 #include "common.cuh"
+#include <cstdlib>
 #include "ops.cuh"
 
 namespace gv {
@@ -1115,6 +1116,8 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, float* ws, size_t ws_floats, const
     if (tiles < 120 && ws) {
         splits = 148 / tiles;  // one wave: 1 CTA per SM (shared memory), never more CTAs than SMs
         splits = min(splits, a.K / 64);
+        static const int min_chunk = [] { const char* e = getenv("GENVC_TC_MIN_KCHUNK"); return e ? atoi(e) : 0; }();  // tuning knob
+        if (min_chunk > 0) splits = min(splits, max(1, a.K / min_chunk));
         while (splits > 1 && (size_t)splits * a.M * a.N > ws_floats) --splits;
         if (splits < 1) splits = 1;
     }

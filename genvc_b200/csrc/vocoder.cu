@@ -395,3 +395,87 @@ extern "C" int genvc_codebook_argmin(const float* x, const float* embed, int64_t
                                                                                                     dim, n_embed, T);
     return cudaGetLastError() == cudaSuccess ? GENVC_OK : GENVC_E_CUDA;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Mel front-end in front of the perceiver (utils.py:95-158 TorchMelSpectrogram = torchaudio MelSpectrogram, power 2, centre /
+// reflect padding, + log(clamp(., 1e-5)) / mel_norms).  One CTA per (frame, batch element): the windowed frame and the
+// n_fft twiddle factors live in shared memory, thread f accumulates bin f by direct summation over the non-zero part of
+// the window (four independent partial sums: shorter dependency chain and smaller rounding growth than one running sum),
+// the power spectrum stays in shared memory, thread m < n_mels applies the filterbank column, log, normalisation.
+// 1.2 GFLOP for 6 s of reference audio at n_fft = 2048 -- the point is one launch and no intermediate tensors, not an FFT.
+// window: [n_fft] (Hann of win_length centred, zeros outside [w_lo, w_hi)); tw: [n_fft][2] = cos, sin(2 pi k / n_fft);
+// fbank: [n_fft / 2 + 1][n_mels]; norms: [n_mels] or NULL; mel: [B, n_mels, T].
+// ---------------------------------------------------------------------------------------------------------------------
+namespace gv {
+__global__ void __launch_bounds__(256)
+mel_frontend_kernel(const float* __restrict__ wav, int N, const float* __restrict__ window, const float* __restrict__ tw,
+                    const float* __restrict__ fbank, const float* __restrict__ norms, float* __restrict__ mel, int n_fft, int hop,
+                    int n_mels, int T, int w_lo, int w_hi, float clamp_min) {
+    extern __shared__ float sm[];
+    float* xs = sm;                 // [n_fft]
+    float* tc = xs + n_fft;         // [n_fft]
+    float* ts = tc + n_fft;         // [n_fft]
+    float* pw = ts + n_fft;         // [n_fft / 2 + 1]
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int n_freq = n_fft / 2 + 1, mask = n_fft - 1;
+    const float* x = wav + (size_t)b * N;
+    for (int n = tid; n < n_fft; n += blockDim.x) {
+        float v = 0.0f;
+        if (n >= w_lo && n < w_hi) {
+            int idx = t * hop + n - n_fft / 2;
+            if (idx < 0) idx = -idx;                      // reflect padding (torch.stft centre=True, pad_mode="reflect")
+            if (idx >= N) idx = 2 * (N - 1) - idx;
+            v = x[idx] * window[n];
+        }
+        xs[n] = v;
+        tc[n] = tw[2 * n];
+        ts[n] = tw[2 * n + 1];
+    }
+    __syncthreads();
+    for (int f = tid; f < n_freq; f += blockDim.x) {
+        float re[4] = {0.f, 0.f, 0.f, 0.f}, im[4] = {0.f, 0.f, 0.f, 0.f};
+        int k = (int)(((long long)f * w_lo) & mask);
+        int n = w_lo;
+        for (; n + 4 <= w_hi; n += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float xv = xs[n + u];
+                re[u] = fmaf(xv, tc[k], re[u]);
+                im[u] = fmaf(xv, ts[k], im[u]);
+                k = (k + f) & mask;
+            }
+        }
+        for (; n < w_hi; ++n) {
+            re[0] = fmaf(xs[n], tc[k], re[0]);
+            im[0] = fmaf(xs[n], ts[k], im[0]);
+            k = (k + f) & mask;
+        }
+        const float r = (re[0] + re[1]) + (re[2] + re[3]), i = (im[0] + im[1]) + (im[2] + im[3]);
+        pw[f] = r * r + i * i;
+    }
+    __syncthreads();
+    for (int m = tid; m < n_mels; m += blockDim.x) {
+        float acc = 0.0f;
+        for (int f = 0; f < n_freq; ++f) acc = fmaf(pw[f], __ldg(fbank + (size_t)f * n_mels + m), acc);
+        float v = logf(fmaxf(acc, clamp_min));
+        if (norms) v /= __ldg(norms + m);
+        mel[((size_t)b * n_mels + m) * T + t] = v;
+    }
+}
+}  // namespace gv
+
+extern "C" int genvc_mel_spectrogram(const float* wav, int B, int N, const float* window, const float* twiddle, const float* fbank,
+                                     const float* norms, float* mel, int n_fft, int hop, int win_lo, int win_hi, int n_mels,
+                                     float clamp_min, void* stream) {
+    if (!wav || !window || !twiddle || !fbank || !mel || B <= 0 || N <= 0 || n_fft < 64 || n_fft > 4096 || (n_fft & (n_fft - 1)) ||
+        hop <= 0 || n_mels <= 0 || win_lo < 0 || win_hi > n_fft || win_lo >= win_hi || N <= n_fft / 2)
+        return GENVC_E_INVALID;  // (reflect padding needs more than n_fft / 2 samples, as torch.stft does)
+    const int T = 1 + N / hop;
+    const size_t smem = ((size_t)3 * n_fft + n_fft / 2 + 1) * sizeof(float);
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(gv::mel_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return GENVC_E_CUDA;
+    gv::mel_frontend_kernel<<<dim3(T, B), 256, smem, (cudaStream_t)stream>>>(wav, N, window, twiddle, fbank, norms, mel, n_fft, hop, n_mels,
+                                                                              T, win_lo, win_hi, clamp_min);
+    return cudaGetLastError() == cudaSuccess ? GENVC_OK : GENVC_E_CUDA;
+}

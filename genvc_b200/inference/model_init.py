@@ -150,7 +150,28 @@ def model_from_checkpoint(ckpt_states: dict, device, max_batch: int = 1, max_mel
     model.gpt.init_gpt_for_inference()
     attach_cuda_hifigan(model, ckpt_states.get("model") or {}, ckpt_states["config"])
     attach_cuda_content_dvae(model, ckpt_states.get("model") or {}, ckpt_states["config"])
+    attach_cuda_mel_frontend(model, config)
     return model, config
+
+
+def attach_cuda_mel_frontend(model, config) -> bool:
+    """The style-encoder mel front-end (``trainers/hifigan_trainer.py:105-115``) on the CUDA library when its normalisation
+    file is available: ``config.model_args.mel_norm_file`` is a readable path (or explicitly None = no normalisation).  A
+    checkpoint whose path does not exist here keeps the attachment point."""
+    import os
+
+    ma = getattr(config, "model_args", None)
+    if ma is None or "mel_norm_file" not in ma or torch.device(model.device).type != "cuda":
+        return False
+    path = ma["mel_norm_file"]
+    if path is not None and not (isinstance(path, str) and os.path.exists(path)):
+        return False
+    from ..mel import TorchMelSpectrogram
+
+    model.torch_mel_spectrogram_style_encoder = TorchMelSpectrogram(
+        filter_length=2048, hop_length=256, win_length=1024, normalize=False, sampling_rate=int(config.audio.sample_rate),
+        mel_fmin=0, mel_fmax=8000, n_mel_channels=80, mel_norm_file=path, device=model.device)
+    return True
 
 
 def attach_cuda_content_dvae(model, state_dict: dict, raw_config) -> bool:

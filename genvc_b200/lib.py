@@ -73,6 +73,7 @@ SIGNATURES = {
     "genvc_launch_count": (C.c_uint64, [_P]),
     "genvc_conv1d": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int] * 8 + [C.c_float, C.c_int, C.c_float, C.c_int, _P, C.c_uint64, _P]),
     "genvc_codebook_argmin": (C.c_int, [_P, _P, _P] + [C.c_int] * 4 + [_P]),
+    "genvc_mel_spectrogram": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, _P]),
     "genvc_conv_transpose1d": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 7 + [C.c_float, _P, C.c_uint64, _P]),
     "genvc_debug_layout": (C.c_int, [_P, _P, C.c_int]),
     "genvc_debug_trace": (C.c_int, [_P, _P, C.c_int, C.c_int]),

@@ -231,6 +231,15 @@ int genvc_conv_transpose1d(const float* x_dev, const float* w_dev, const float* 
 int genvc_codebook_argmin(const float* x_dev, const float* embed_dev, int64_t* codes_dev, int B, int dim, int n_embed, int T,
                           void* stream);
 
+/* Mel front-end of the conditioning path (utils.py:95-158 TorchMelSpectrogram; a1 = trainers/hifigan_trainer.py:438-455 calls
+ * it on every 6 s chunk of the reference audio): torchaudio MelSpectrogram (power 2, centre / reflect padding, window centred
+ * in n_fft) + log(clamp(., clamp_min)) / norms.  wav [B, N] -> mel [B, n_mels, 1 + N / hop].  Tables are caller-built
+ * (genvc_b200/mel.py): window [n_fft] (zeros outside [win_lo, win_hi)), twiddle [n_fft][2] = cos, sin(2 pi k / n_fft),
+ * fbank [n_fft / 2 + 1][n_mels] (torchaudio.functional.melscale_fbanks), norms [n_mels] or NULL.  n_fft: power of two <= 4096. */
+int genvc_mel_spectrogram(const float* wav_dev, int B, int N, const float* window_dev, const float* twiddle_dev,
+                          const float* fbank_dev, const float* norms_dev, float* mel_dev, int n_fft, int hop, int win_lo,
+                          int win_hi, int n_mels, float clamp_min, void* stream);
+
 /* Post-mortem aid (tools/hang_dump.py): byte offsets inside the workspace of the fused decode kernel's exchange buffers and
  * arrival counters: out[0..11] = xq, att_o, att_ml, x1, pp, x2, lg, hops, sbuf offsets, then grid, counter stride (words),
  * number of counters.  The buffers hold {value, tag} pairs; reading them from a side stream while a launch is stuck shows

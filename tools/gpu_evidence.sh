@@ -16,17 +16,19 @@ cap() {  # name regex skip extra-args...
 }
 cap decode_mega decode_mega 4 python bench.py --steps 2 --warmup 3 --no-cpu
 cap gemm_tc gemm_tc_kernel 400 python bench.py --steps 2 --warmup 3 --no-cpu
-cap attention "attention_kernel" 40 python bench.py --steps 2 --warmup 3 --no-cpu
+cap attention "attention_row_kernel" 40 python bench.py --steps 2 --warmup 3 --no-cpu
 cap splitk_ln splitk_ln_epilogue 40 python bench.py --steps 2 --warmup 3 --no-cpu
 cap decode_batch decode_batch 2 python tools/batch_bench.py --rows 8 --tokens 12
 cap kv_attention kv_attention_kernel 10 python tools/kv_bench.py
 ls -la $OUT
 cap pc_attention_tc pc_attention_tc 2 python bench.py --steps 2 --warmup 3 --no-cpu
+cap vocoder_conv1d conv1d_kernel 70 python tools/vocoder_bench.py --no-cpu --reps 2
 # 3. bench lines of the three workloads (no profiler), phase timeline of the single-row kernel
 timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
 timeout 600 python bench.py --config cfg3 --no-cpu > $OUT/bench_cfg3.json 2> $OUT/bench_cfg3.err; echo "bench cfg3 exit $?"
 timeout 600 python bench.py --config cfg4 --no-cpu > $OUT/bench_cfg4.json 2> $OUT/bench_cfg4.err; echo "bench cfg4 exit $?"
 timeout 300 python tools/timeline.py > $OUT/timeline.txt 2>&1; echo "timeline exit $?"
 timeout 300 python tools/batch_bench.py --rows 8 --tokens 64 > $OUT/batch_bench.json 2>&1; echo "batch bench exit $?"
+timeout 300 python tools/vocoder_bench.py > $OUT/stage_bench.json 2> $OUT/stage_bench.err; echo "stage bench exit $?"
 rm -f $OUT/*.ncu-rep.tmp
 ls -la $OUT

@@ -25,7 +25,7 @@ tag = sys.argv[1]
 src = os.path.join(ROOT, "gpurun_out", tag)
 dst = os.path.join(ROOT, "profiles", tag)
 os.makedirs(dst, exist_ok=True)
-for f in ("gpu.txt", "bench.json", "bench_cfg3.json", "bench_cfg4.json", "timeline.txt", "batch_bench.json"):
+for f in ("gpu.txt", "bench.json", "bench_cfg3.json", "bench_cfg4.json", "timeline.txt", "batch_bench.json", "stage_bench.json"):
     if os.path.exists(os.path.join(src, f)):
         shutil.copy(os.path.join(src, f), dst)
 
@@ -76,7 +76,8 @@ NOTES = {
     "decode_mega": "fused single-row decode kernel, one launch = stream_chunk_size forwards (bench.py --steps 2 --warmup 3 --no-cpu)",
     "decode_batch": "fused batched decode kernel, 8 rows x 11 forwards (tools/batch_bench.py --rows 8 --tokens 12)",
     "gemm_tc": "tcgen05 3xTF32 GEMM of the prefill (48 rows)",
-    "attention": "causal attention of the prefill (48 rows x 4 heads x 256)",
+    "attention": "causal attention of the prefill (48 rows x 4 heads x 256): one CTA per (row, head)",
+    "vocoder_conv1d": "HiFi-GAN generator / content-DVAE convolution (tools/vocoder_bench.py)",
     "splitk_ln": "split-K reduction + bias + residual + LayerNorm epilogue of the prefill GEMMs",
     "kv_attention": "single-query KV-cache attention (BASELINE configs[4] microbenchmark)",
     "pc_attention_tc": "perceiver cross-attention on tcgen05 (one CTA per element and head)",

@@ -81,3 +81,25 @@ for label, T in (("segment_1s", 50), ("segment_6s", 300)):
     torch.cuda.synchronize()
     dres[label] = {"frames": T, "codes": (T + 3) // 4, "ms": round(e0.elapsed_time(e1) / a.reps, 4)}
 print(json.dumps({"content_dvae": dres}))
+
+# ---- mel front-end of the conditioning path (style encoder: n_fft 2048, hop 256, win 1024, 24 kHz)
+from genvc_b200.mel import TorchMelSpectrogram
+mf = TorchMelSpectrogram(filter_length=2048, hop_length=256, win_length=1024, sampling_rate=24000, n_mel_channels=80, device=dev)
+mres = {}
+for label, n in (("audio_6s", 144000), ("audio_30s", 720000)):
+    w = torch.randn(1, n, device=dev) * 0.1
+    for _ in range(3):
+        mf(w)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        mf(w)
+    e1.record()
+    torch.cuda.synchronize()
+    r = {"samples": n, "frames": 1 + n // 256, "ms": round(e0.elapsed_time(e1) / a.reps, 4)}
+    if not a.no_cpu and n <= 144000:
+        from oracle.mel_oracle import log_mel
+        r["max_err_vs_oracle"] = float((mf(w).cpu() - log_mel(w.cpu(), 2048, 256, 1024, 80, 0, 8000, 24000)).abs().max())
+    mres[label] = r
+print(json.dumps({"mel_frontend": mres}))
