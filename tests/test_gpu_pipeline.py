@@ -265,3 +265,59 @@ def test_batched_segments_driver_matches_serial(cuda_device):
         b = drv.synthesize_utt(model, src.clone(), tgt.clone(), reuse_decode_latents=fold, batch_segments=True)
         assert a.shape == b.shape, (a.shape, b.shape)
         assert (a - b).abs().max() < 2e-3
+
+
+@pytest.mark.gpu
+def test_pipeline_with_every_cuda_stage_matches_oracle(cuda_device):
+    """The whole conversion on the device except ContentVec (fairseq, absent: a stub): CUDA mel front-end -> perceiver ->
+    content-DVAE tokeniser -> GPT prefill / fused decode -> x4 interpolation -> CUDA HiFi-GAN generator, driven by
+    synthesize_utt / synthesize_utt_streaming, against the CPU oracles of every stage chained the same way (greedy)."""
+    from genvc_b200.content_dvae import DiscreteVAE
+    from genvc_b200.inference import inference_utils as drv
+    from genvc_b200.mel import TorchMelSpectrogram
+    from genvc_b200.synth import HIFIGAN_DEFAULTS, synth_dvae_state, synth_hifigan_state
+    from genvc_b200.vocoder import HiFiGAN
+    from oracle.dvae_oracle import get_codebook_indices
+    from oracle.genvc_oracle import SamplingParams, load_oracle
+    from oracle.hifigan_oracle import vocode
+    from oracle.mel_oracle import log_mel
+
+    fx = load_golden("toy_d128_eos")
+    model, cfg, ck = _model(fx, cuda_device)
+    dv_cfg = dict(channels=3, num_tokens=256, codebook_dim=32, hidden_dim=16, num_resnet_blocks=1)
+    dv_sd = synth_dvae_state(21, **dv_cfg)
+    hf_cfg = dict(input_feat_dim=128, upsample_initial_channel=32)
+    hf_sd = synth_hifigan_state(22, **hf_cfg)
+    model.content_extractor = _StubStages()  # ContentVec stand-in: [B, T50Hz, 3]
+    model.content_dvae = DiscreteVAE(positional_dims=1, kernel_size=3, num_layers=2, use_transposed_convs=False, device=cuda_device,
+                                     **dv_cfg).load_state_dict(dv_sd)
+    arch = dict(HIFIGAN_DEFAULTS, **hf_cfg)
+    model.hifigan = HiFiGAN(arch["input_feat_dim"], arch["upsample_initial_channel"], arch["resblock_kernel_sizes"],
+                            arch["resblock_dilation_sizes"], arch["upsample_rates"], arch["upsample_kernel_sizes"], arch["resblock_type"],
+                            device=cuda_device).load_state_dict(hf_sd)
+    model.torch_mel_spectrogram_style_encoder = TorchMelSpectrogram(filter_length=2048, hop_length=256, win_length=1024, sampling_rate=SR,
+                                                                    n_mel_channels=80, device=cuda_device)
+    cfg.top_k, cfg.top_p, cfg.temperature, cfg.repetition_penalty = 1, 0.85, 0.85, 2.0
+    g = torch.Generator().manual_seed(9)
+    src = torch.randn(1, int(7.1 * 16000), generator=g)
+    tgt = torch.randn(1, int(6.6 * SR), generator=g) * 0.3
+    wav = drv.synthesize_utt(model, src.clone(), tgt.clone())
+    pieces = []
+    wav_stream = drv.synthesize_utt_streaming(model, src.clone(), tgt.clone(), stream_chunk_size=8, on_chunk=pieces.append)
+
+    o = load_oracle(ck)
+    cond = o.get_gpt_cond_latents([log_mel(ch.unsqueeze(0), 2048, 256, 1024, 80, 0, 8000, SR) for ch in reference_chunks(tgt, SR)])
+    sp = SamplingParams(top_k=1, top_p=0.85, temperature=0.85, repetition_penalty=2.0)
+    lat2 = []
+    hf_arch = {k: arch[k] for k in ("resblock_kernel_sizes", "resblock_dilation_sizes", "upsample_rates", "upsample_kernel_sizes", "resblock_type")}
+    for start, end, pad in drv.plan_segments(src.shape[-1], 96000, 5120):
+        seg = torch.nn.functional.pad(src[:, start:end], (0, pad))
+        feat = _StubStages.extract_content_features(seg)
+        codes = get_codebook_indices(dv_sd, feat.transpose(1, 2), num_layers=2, num_resnet_blocks=1, kernel_size=3)
+        ids, _ = o.generate(cond, codes, sp)
+        keep = ids[0] != 1025
+        lat2.append(o.forward_latents(codes, ids[0][keep][None], cond))
+    ref_wav = vocode(hf_sd, torch.cat(lat2, dim=1), 4.0, **hf_arch)[0].squeeze()
+    assert wav.shape == ref_wav.shape
+    assert (wav.cpu() - ref_wav).abs().max() < 2e-3
+    assert wav_stream.ndim == 1 and len(pieces) >= 2
