@@ -95,10 +95,13 @@ class Engine:
             self.ws = torch.zeros(int(self.lib.genvc_workspace_bytes(self._ctx)), dtype=torch.uint8, device=self.device)
         self._check(self.lib.genvc_bind_buffers(self._ctx, self.kv.data_ptr(), self.kv.numel(), self.ws.data_ptr(),
                                                 self.ws.numel()))
-        # projected-value cache of the single-row fused kernel (0.6 GB at L=30, H=4; GENVC_VW=0 keeps the K / V items)
+        # projected-value cache variant of the single-row fused kernel: opt-in (GENVC_VW=1).  Since the GEMV weights are in
+        # registers before their hop (gemv_preload) the K / V attention items win at every length measured: 6 s segment, 140
+        # tokens, S up to 250: 0.404 ms/token against 0.509 with the cache, whose weighted sum reads (S - 1) x H rows of 32
+        # bytes per CTA and only the first 256 of them are prefetched (tools/long_gen_bench.py).  1.07 GB at L=30, H=4.
         self.vw: Optional[torch.Tensor] = None
         n_vw = int(self.lib.genvc_vw_floats(self._ctx))
-        if n_vw > 0 and os.environ.get("GENVC_VW", "1") != "0":
+        if n_vw > 0 and os.environ.get("GENVC_VW", "0") == "1":
             with torch.cuda.device(self.device):
                 self.vw = torch.zeros(n_vw, dtype=torch.float32, device=self.device)
             self._check(self.lib.genvc_bind_vw(self._ctx, self.vw.data_ptr(), n_vw))

@@ -170,6 +170,7 @@ def test_projected_value_variant_matches_fixtures(name, cuda_device, monkeypatch
     from genvc_b200.engine import Sampling
     from genvc_b200.gpt import GPT
 
+    monkeypatch.setenv("GENVC_VW", "1")  # the variant is opt-in
     monkeypatch.setenv("GENVC_VW_MIN_TOKENS", "1")
     fx = load_golden(name)
     ck = golden_checkpoint(fx)
