@@ -9,6 +9,7 @@ codebook entry in ``genvc_codebook_argmin``.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List
 
 import torch
@@ -35,7 +36,7 @@ class DiscreteVAE:
         self._embed = None
         self._scratch = torch.empty(2 * 1024 * 1024, dtype=torch.float32, device=self.device)
         self._graphs: Dict[tuple, tuple] = {}
-        self.use_graphs = True
+        self.use_graphs = os.environ.get("GENVC_STAGE_GRAPHS", "1") != "0"  # 0: every call launches its kernels eagerly
         self.launches = 0
 
     def eval(self):

@@ -10,6 +10,7 @@ bias, residual, resblock sum and tanh fused into the convolutions — ``csrc/voc
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -59,7 +60,7 @@ class HiFiGAN:
         self.lib = load_library()
         self._convs: Dict[str, _Conv] = {}
         self._graphs: Dict[Tuple[int, int], tuple] = {}
-        self.use_graphs = True
+        self.use_graphs = os.environ.get("GENVC_STAGE_GRAPHS", "1") != "0"  # 0: every call launches its kernels eagerly
         self.launches = 0
         # split-over-input-channels partial sums of the small layers (csrc/vocoder.cu: pick_ksplit); 8 MB covers 16 slices of
         # the largest layer that is ever split at streaming sizes
