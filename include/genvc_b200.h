@@ -201,7 +201,8 @@ uint64_t genvc_launch_count(const genvc_ctx* ctx);
 int genvc_debug_trace(genvc_ctx* ctx, uint64_t* trace_dev, int slots_per_cta, int step);
 
 /* ---- the stage after the path: HiFi-GAN generator building blocks ----
- * Stateless (no context); device pointers; fp32; layouts [B, C, T].  The host side (genvc_b200/vocoder.py) strings them
+ * Stateless (no context): the kernels are enqueued on `stream` of the CALLER'S CURRENT device, which must own every
+ * pointer (the host classes wrap their calls in the device of their tensors); device pointers; fp32; layouts [B, C, T].  The host side (genvc_b200/vocoder.py) strings them
  * together as layers/hifigan.py:210-225 does.  Weights are passed REPACKED to [Cin][K][Cout]
  * (reference: Conv1d weight [Cout][Cin][K] -> permute(1,2,0); ConvTranspose1d weight [Cin][Cout][K] -> permute(0,2,1)),
  * weight norm already folded (w = g * v / ||v||).
