@@ -82,6 +82,14 @@ struct genvc_ctx {
         unsigned long long launches = 0;
     };
     std::map<std::pair<int, int>, PrefillGraph> prefill_graphs;
+    std::map<std::pair<int, int>, PrefillGraph> perceiver_graphs;  // the perceiver's ~45 launches, per (batch, mel frames)
+    void drop_graphs() {  // captured launches bake workspace / weight pointers
+        for (auto* m : {&prefill_graphs, &perceiver_graphs}) {
+            for (auto& kv : *m)
+                if (kv.second.exec) (void)cudaGraphExecDestroy(kv.second.exec);
+            m->clear();
+        }
+    }
     bool use_graphs = true;
     bool pc_attention_tc = true;  // perceiver cross-attention on tcgen05 (GENVC_PC_TC=0: CUDA-core attention kernel)
     // persistent fused prefill (gemm_tc.cu): device table of the packed tensor-core weights of the blocks
@@ -273,8 +281,7 @@ int genvc_create(const genvc_config* cfg, int device, genvc_ctx** out) {
 void genvc_destroy(genvc_ctx* ctx) {
     if (!ctx) return;
     if (ctx->blob) gemm_tc_forget(ctx->blob, ctx->blob + ctx->layout.total);
-    for (auto& kv : ctx->prefill_graphs)
-        if (kv.second.exec) (void)cudaGraphExecDestroy(kv.second.exec);
+    ctx->drop_graphs();
     delete ctx;
 }
 
@@ -384,9 +391,7 @@ int genvc_bind_weights(genvc_ctx* ctx, const float* blob_dev, uint64_t n_floats)
     ctx->stream_packed = false;
     ctx->tc_table.clear();
     ctx->tc_table_uploaded = false;
-    for (auto& kv : ctx->prefill_graphs)  // captured launches hold the old pointers
-        if (kv.second.exec) (void)cudaGraphExecDestroy(kv.second.exec);
-    ctx->prefill_graphs.clear();
+    ctx->drop_graphs();
     return GENVC_OK;
 }
 
@@ -441,9 +446,7 @@ int genvc_bind_vw(genvc_ctx* ctx, float* vw_dev, uint64_t n_floats) {
         ctx->vw = vw_dev;
     }
     ctx->prefilled = false;
-    for (auto& kv : ctx->prefill_graphs)  // captured prefills bake the pointer (and whether the cache is filled at all)
-        if (kv.second.exec) (void)cudaGraphExecDestroy(kv.second.exec);
-    ctx->prefill_graphs.clear();
+    ctx->drop_graphs();
     return GENVC_OK;
 }
 
@@ -459,9 +462,7 @@ int genvc_bind_buffers(genvc_ctx* ctx, float* kv_dev, uint64_t kv_floats, void* 
     ctx->kv = kv_dev;
     ctx->ws = static_cast<char*>(workspace_dev);
     ctx->prefilled = false;
-    for (auto& kv : ctx->prefill_graphs)
-        if (kv.second.exec) (void)cudaGraphExecDestroy(kv.second.exec);
-    ctx->prefill_graphs.clear();
+    ctx->drop_graphs();
     // exchange tags start at 1 over zeroed buffers
     DevGuard guard(ctx->device);
     CK(guard.err);
@@ -602,6 +603,46 @@ static int run_head(genvc_ctx* ctx, int B, int M, int row, const int* skip, cuda
     return GENVC_OK;
 }
 
+// Runs `body` (a sequence of launches on `st` that only touches context-owned buffers) -- eagerly the first time a key is
+// seen (sets kernel attributes, warms caches), captured into a CUDA graph on a second pass, replayed from then on.
+template <class Body>
+static int run_or_replay(genvc_ctx* ctx, std::map<std::pair<int, int>, genvc_ctx::PrefillGraph>& cache, std::pair<int, int> key,
+                         cudaStream_t st, Body body) {
+    if (!ctx->use_graphs) return body();
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        if (it->second.exec == nullptr) return body();  // capture failed once for this shape: per-op launches
+        CK(cudaGraphLaunch(it->second.exec, st));
+        ctx->nlaunch += it->second.launches;
+        return GENVC_OK;
+    }
+    if (int rc = body()) return rc;
+    genvc_ctx::PrefillGraph pg;
+    const unsigned long long l0 = ctx->nlaunch;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        const int rc = body();
+        const cudaError_t e = cudaStreamEndCapture(st, &graph);
+        ok = rc == GENVC_OK && e == cudaSuccess && graph != nullptr;
+    }
+    pg.launches = ctx->nlaunch - l0;
+    ctx->nlaunch = l0;  // nothing ran during the capture
+    if (ok) ok = cudaGraphInstantiate(&pg.exec, graph, 0) == cudaSuccess;
+    if (graph) (void)cudaGraphDestroy(graph);
+    if (!ok) {
+        (void)cudaGetLastError();
+        pg.exec = nullptr;
+    }
+    if (cache.size() >= 64) {  // bounded cache
+        for (auto& kv : cache)
+            if (kv.second.exec) (void)cudaGraphExecDestroy(kv.second.exec);
+        cache.clear();
+    }
+    cache[key] = pg;
+    return GENVC_OK;  // the eager pass above did the work
+}
+
 extern "C" {
 
 // ---------------------------------------------------------------------------------------------
@@ -633,7 +674,8 @@ int genvc_perceiver(genvc_ctx* ctx, const float* mel_dev, int B, int S_mel, floa
     unsigned long long* nl = &ctx->nlaunch;
 
     const int Cp = (int)L.pc_ctx_pad;  // mel channels zero-padded to the k granularity of the tensor-core GEMM
-    CK(launch_transpose_mel(mel_dev, B, C, Cp, S_mel, melT, st, nl));
+    CK(launch_transpose_mel(mel_dev, B, C, Cp, S_mel, melT, st, nl));  // (caller's pointer: outside the replayed part)
+    auto body = [&]() -> int {
     for (int b = 0; b < B; ++b)  // proj_context into rows NL.. of this element's context block
         CK(launch_gemm(gemm(melT + (size_t)b * S_mel * Cp, Cp, ctx->w(L.pc_proj_w), Cp, 1, ctx->w(L.pc_proj_b), nullptr, 0,
                             cx + ((size_t)b * RC + NL) * D, D, S_mel, D, Cp, ACT_NONE),
@@ -668,6 +710,9 @@ int genvc_perceiver(genvc_ctx* ctx, const float* mel_dev, int B, int S_mel, floa
         CK(launch_gemm(gemm(gb, ffp, ctx->w(o.ff2_w), ffp, 1, ctx->w(o.ff2_b), lat, D, lat, D, B * NL, D, ffp, ACT_NONE), sk,
                        kSplitKFloats, nullptr, st, nl));
     }
+    return GENVC_OK;
+    };
+    if (int rc = run_or_replay(ctx, ctx->perceiver_graphs, std::make_pair(B, S_mel), st, body)) return rc;
     CK(launch_rmsnorm(lat, latents_out_dev, B * NL, D, ctx->w(L.pc_gamma), st, nl));
     return GENVC_OK;
 }
